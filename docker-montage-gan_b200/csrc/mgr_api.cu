@@ -1,0 +1,117 @@
+// C ABI of libmontage_render.so -- argument validation and kernel dispatch.
+// Declarations and the reference interfaces they replace: include/montage_render.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+
+#include "montage_render.h"
+#include "mgr_common.cuh"
+#include "mgr_errors.h"
+
+#include "launchers_decl.h"
+
+namespace {
+thread_local char g_err[512] = "";
+}
+
+namespace mgr {
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  return fail(MGR_ERR_CUDA_BASE + (int)e, "%s: %s", what, cudaGetErrorString(e));
+}
+}  // namespace mgr
+
+namespace {
+using mgr::fail;
+
+int check_common(const void* x, const int64_t* xs, int B, int L, int H, int W, int dtype, int range_mode,
+                 mgr::Geometry* g) {
+  if (!x) return fail(MGR_ERR_INVALID_ARGUMENT, "x is NULL");
+  if (B < 0 || L < 1 || H < 1 || W < 1)
+    return fail(MGR_ERR_INVALID_ARGUMENT, "bad shape B=%d L=%d H=%d W=%d (need B>=0, L,H,W>=1)", B, L, H, W);
+  if (dtype != MGR_F32 && dtype != MGR_BF16 && dtype != MGR_F16)
+    return fail(MGR_ERR_INVALID_ARGUMENT, "bad dtype %d", dtype);
+  if (range_mode != MGR_RANGE_M11 && range_mode != MGR_RANGE_01)
+    return fail(MGR_ERR_INVALID_ARGUMENT, "bad range_mode %d", range_mode);
+  if (B > 65535) return fail(MGR_ERR_UNSUPPORTED, "B=%d exceeds 65535 per call; split the batch", B);
+  if (L > 32) return fail(MGR_ERR_UNSUPPORTED, "L=%d exceeds 32 layers", L);
+  g->B = B; g->L = L; g->H = H; g->W = W;
+  g->m11 = (range_mode == MGR_RANGE_M11);
+  if (xs) {
+    if (xs[4] != 1) return fail(MGR_ERR_UNSUPPORTED, "x stride along W must be 1 (got %lld)", (long long)xs[4]);
+    g->sb = xs[0]; g->sl = xs[1]; g->sc = xs[2]; g->sh = xs[3];
+  } else {
+    g->sh = W; g->sc = (long long)H * W; g->sl = 4 * g->sc; g->sb = (long long)L * g->sl;
+  }
+  if (g->sh < W || g->sh * (long long)H > 0x7fffffffLL)
+    return fail(MGR_ERR_UNSUPPORTED, "row stride %lld out of range for H=%d W=%d", g->sh, H, W);
+  return MGR_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mgr_abi_version(void) { return MGR_ABI_VERSION; }
+
+#define MGR_STR2(v) #v
+#define MGR_STR(v) MGR_STR2(v)
+const char* mgr_build_info(void) {
+  return "libmontage_render abi " MGR_STR(MGR_ABI_VERSION) " sm_100a cuda " MGR_STR(__CUDACC_VER_MAJOR__) "." MGR_STR(
+      __CUDACC_VER_MINOR__) " built " __DATE__ " " __TIME__;
+}
+
+const char* mgr_last_error(void) { return g_err; }
+
+int mgr_render_forward(const void* x, const int64_t* x_strides, const float* theta, void* out, int B, int L, int H,
+                       int W, int dtype, int range_mode, void* stream) {
+  mgr::Geometry g;
+  if (int rc = check_common(x, x_strides, B, L, H, W, dtype, range_mode, &g)) return rc;
+  if (!out) return fail(MGR_ERR_INVALID_ARGUMENT, "out is NULL");
+  if (B == 0) return MGR_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case MGR_F32: return mgr_fwd_f32(x, theta, out, g, s);
+    case MGR_BF16: return mgr_fwd_bf16(x, theta, out, g, s);
+    default: return mgr_fwd_f16(x, theta, out, g, s);
+  }
+}
+
+size_t mgr_render_backward_workspace_bytes(int B, int L, int H, int W, int dtype, int has_theta, int flags) {
+  if (B <= 0 || L <= 0 || H <= 0 || W <= 0) return 0;
+  if (has_theta && (flags & MGR_NEED_GRAD_X) && dtype != MGR_F32)
+    return sizeof(float) * (size_t)B * L * 4 * H * W;   // fp32 scatter accumulator
+  return 0;
+}
+
+int mgr_render_backward(const void* x, const int64_t* x_strides, const float* theta, const void* out,
+                        const void* grad_out, void* grad_x, float* grad_theta, void* workspace,
+                        size_t workspace_bytes, int B, int L, int H, int W, int dtype, int range_mode, int flags,
+                        void* stream) {
+  mgr::Geometry g;
+  if (int rc = check_common(x, x_strides, B, L, H, W, dtype, range_mode, &g)) return rc;
+  if (!out || !grad_out) return fail(MGR_ERR_INVALID_ARGUMENT, "out / grad_out is NULL");
+  if (!theta) flags &= ~MGR_NEED_GRAD_THETA;
+  if ((flags & MGR_NEED_GRAD_X) && !grad_x) return fail(MGR_ERR_INVALID_ARGUMENT, "grad_x is NULL but requested");
+  if ((flags & MGR_NEED_GRAD_THETA) && !grad_theta)
+    return fail(MGR_ERR_INVALID_ARGUMENT, "grad_theta is NULL but requested");
+  if (!(flags & (MGR_NEED_GRAD_X | MGR_NEED_GRAD_THETA)) || B == 0) return MGR_OK;
+  const size_t need = mgr_render_backward_workspace_bytes(B, L, H, W, dtype, theta != nullptr, flags);
+  if (need > 0 && (!workspace || workspace_bytes < need))
+    return fail(MGR_ERR_WORKSPACE_TOO_SMALL, "workspace %zu bytes < required %zu", workspace_bytes, need);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case MGR_F32: return mgr_bwd_f32(x, theta, out, grad_out, grad_x, grad_theta, workspace, g, flags, s);
+    case MGR_BF16: return mgr_bwd_bf16(x, theta, out, grad_out, grad_x, grad_theta, workspace, g, flags, s);
+    default: return mgr_bwd_f16(x, theta, out, grad_out, grad_x, grad_theta, workspace, g, flags, s);
+  }
+}
+
+}  // extern "C"

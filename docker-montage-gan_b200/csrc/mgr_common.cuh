@@ -1,0 +1,102 @@
+// Shared device helpers for the montage renderer kernels (sm_100a).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mgr {
+
+// ---- element access: storage dtype <-> fp32 registers -------------------------------------
+template <typename T> __device__ __forceinline__ float ld(const T* p);
+template <> __device__ __forceinline__ float ld<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float ld<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __uint_as_float(static_cast<uint32_t>(__ldg(reinterpret_cast<const unsigned short*>(p))) << 16);
+}
+template <> __device__ __forceinline__ float ld<__half>(const __half* p) {
+  return __half2float(__ushort_as_half(__ldg(reinterpret_cast<const unsigned short*>(p))));
+}
+
+template <typename T> __device__ __forceinline__ void st(T* p, float v);
+template <> __device__ __forceinline__ void st<float>(float* p, float v) { *p = v; }
+template <> __device__ __forceinline__ void st<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ void st<__half>(__half* p, float v) { *p = __float2half_rn(v); }
+
+// ---- problem description handed to every kernel -------------------------------------------
+struct Geometry {
+  int B, L, H, W;
+  long long sb, sl, sc, sh;  // element strides of x for [B,L,4,H,W]; W stride is 1
+  int m11;                   // 1: [-1,1] range mode, 0: [0,1]
+};
+
+// Pixel-space placement of one layer relative to a tile origin (j0,i0), SURVEY.md A.1:
+//   ix(j,i) = a00*(j-j0) + a01*(i-i0) + (X0 + rx),  iy likewise.
+// The integer part X0/Y0 is split off in double precision so the fp32 per-pixel arithmetic only
+// carries tile-local magnitudes (fraction accurate to ~1e-6 px instead of ulp(256) = 3e-5 px).
+struct TileAffine {
+  float a00, a01, rx;
+  float a10, a11, ry;
+  int X0, Y0;
+};
+
+__device__ __forceinline__ TileAffine make_tile_affine(const float* __restrict__ th, int H, int W,
+                                                       int j0, int i0) {
+  // theta maps normalised output coords to normalised input coords (align_corners=False):
+  //   gx = t00*x_j + t01*y_i + t02,  x_j = (2j+1)/W - 1,  ix = ((gx+1)*W - 1)/2
+  // => ix = t00*(j + .5 - W/2) + t01*(W/H)*(i + .5 - H/2) + t02*W/2 + (W-1)/2
+  const double t00 = th[0], t01 = th[1], t02 = th[2], t10 = th[3], t11 = th[4], t12 = th[5];
+  const double w = W, h = H;
+  const double a00 = t00, a01 = t01 * (w / h);
+  const double a10 = t10 * (h / w), a11 = t11;
+  double cx = a00 * (j0 + 0.5 - 0.5 * w) + a01 * (i0 + 0.5 - 0.5 * h) + t02 * 0.5 * w + 0.5 * (w - 1.0);
+  double cy = a10 * (j0 + 0.5 - 0.5 * w) + a11 * (i0 + 0.5 - 0.5 * h) + t12 * 0.5 * h + 0.5 * (h - 1.0);
+  // keep the integer split representable for absurd thetas (NaN falls through the min/max as-is)
+  cx = fmin(fmax(cx, -1.0e9), 1.0e9);
+  cy = fmin(fmax(cy, -1.0e9), 1.0e9);
+  const double fx = floor(cx), fy = floor(cy);
+  TileAffine t;
+  t.a00 = (float)a00; t.a01 = (float)a01; t.a10 = (float)a10; t.a11 = (float)a11;
+  t.X0 = (int)fx; t.Y0 = (int)fy;
+  t.rx = (float)(cx - fx); t.ry = (float)(cy - fy);
+  return t;
+}
+
+// Four in-bounds-masked bilinear taps of one channel plane.
+struct Taps {
+  int o00, o01, o10, o11;        // element offsets inside an x plane (valid only if the mask bit is set)
+  int x0, y0;                    // integer tap origin (top-left), may be outside the image
+  float w00, w01, w10, w11;      // bilinear weights (not masked)
+  float fx, fy;
+  unsigned mask;                 // bit0..3: tap 00,01,10,11 inside the image
+};
+
+__device__ __forceinline__ Taps make_taps(const TileAffine& t, int dj, int di, int H, int W, long long sh) {
+  const float ix = fmaf(t.a00, (float)dj, fmaf(t.a01, (float)di, t.rx));
+  const float iy = fmaf(t.a10, (float)dj, fmaf(t.a11, (float)di, t.ry));
+  const float fxf = floorf(ix), fyf = floorf(iy);
+  Taps p;
+  p.fx = ix - fxf; p.fy = iy - fyf;
+  // saturating float->int conversion keeps huge coordinates out of range instead of wrapping
+  const int x0 = t.X0 + __float2int_rd(fminf(fmaxf(fxf, -1.0e9f), 1.0e9f));
+  const int y0 = t.Y0 + __float2int_rd(fminf(fmaxf(fyf, -1.0e9f), 1.0e9f));
+  const bool xin0 = (unsigned)x0 < (unsigned)W, xin1 = (unsigned)(x0 + 1) < (unsigned)W;
+  const bool yin0 = (unsigned)y0 < (unsigned)H, yin1 = (unsigned)(y0 + 1) < (unsigned)H;
+  p.mask = (xin0 && yin0 ? 1u : 0u) | (xin1 && yin0 ? 2u : 0u) | (xin0 && yin1 ? 4u : 0u) | (xin1 && yin1 ? 8u : 0u);
+  const int base = y0 * (int)sh + x0;   // plane offsets fit in int (H*W <= 2^31 enforced by the API)
+  p.x0 = x0; p.y0 = y0;
+  p.o00 = base; p.o01 = base + 1; p.o10 = base + (int)sh; p.o11 = base + (int)sh + 1;
+  const float ex = 1.f - p.fx, ey = 1.f - p.fy;
+  p.w00 = ex * ey; p.w01 = p.fx * ey; p.w10 = ex * p.fy; p.w11 = p.fx * p.fy;
+  return p;
+}
+
+// normalised output coordinate of pixel index k along an axis of size n: (2k+1)/n - 1
+__device__ __forceinline__ float norm_coord(int k, int n) { return (float)(2 * k + 1) / (float)n - 1.f; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace mgr

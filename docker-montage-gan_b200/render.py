@@ -1,0 +1,135 @@
+"""Host side of the analytic renderer: ``torch.autograd.Function`` wrappers over the C ABI.
+
+Public functions mirror the reference's own names and tensor conventions (paths relative to
+/root/reference/montage_gan):
+
+* ``render(x, theta)``                -- the chain ``STNv2c`` warp (``fukuwarai/networks.py:250-257``)
+  -> ``normalize_minus11(alpha_composite_pytorch(normalize_zero1(.)))`` (``custom/loss_aio.py:251``)
+  fused into one kernel; ``theta=None`` is the composite-only real branch (``loss_aio.py:313-320``).
+* ``alpha_composite_pytorch(blchw)``  -- drop-in for ``custom_utils/image_utils.py:112-163``
+  (default branch; [0,1] range; accepts [B,L,4,H,W] or [L,4,H,W]).
+
+PyTorch is plumbing here (device memory, streams, autograd graph); all arithmetic happens in
+libmontage_render.so.  There is no CPU path: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.MGR_F32, torch.bfloat16: _lib.MGR_BF16, torch.float16: _lib.MGR_F16}
+_RANGES = {"m11": _lib.MGR_RANGE_M11, "01": _lib.MGR_RANGE_01}
+
+
+def _ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _check_inputs(x, theta, in_range):
+    if not isinstance(x, torch.Tensor):
+        raise TypeError("x must be a torch.Tensor")
+    if x.dim() != 5 or x.shape[2] != 4:
+        raise ValueError(f"x must be [B,L,4,H,W] (RGBA layers), got {tuple(x.shape)}")
+    if x.dtype not in _DTYPES:
+        raise TypeError(f"x dtype {x.dtype} not supported (float32, bfloat16, float16)")
+    if in_range not in _RANGES:
+        raise ValueError(f"in_range must be 'm11' or '01', got {in_range!r}")
+    B, L = x.shape[:2]
+    if L < 1:
+        raise ValueError("x needs at least one layer")
+    if theta is not None:
+        if tuple(theta.shape) != (B, L, 2, 3):
+            raise ValueError(f"theta must be [B,L,2,3] = {(B, L, 2, 3)}, got {tuple(theta.shape)}")
+        if theta.device != x.device:
+            raise ValueError("theta must live on the same device as x")
+    if not x.is_cuda:
+        raise _lib.MontageRenderError("x must be a CUDA tensor: the renderer has no CPU path")
+
+
+def _x_arg(x):
+    """Pass x through untouched whenever the innermost stride is 1 (any batch / layer / channel /
+    row strides are handled by the kernels); only a W-strided view is compacted."""
+    if x.stride(4) != 1 and x.shape[4] > 1:
+        x = x.contiguous()
+    strides = None if x.is_contiguous() else _lib.strides_arg(x.stride()[:4] + (1,))
+    return x, strides
+
+
+class _Render(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, theta, in_range):
+        lib = _lib.load()
+        B, L, _, H, W = x.shape
+        xk, strides = _x_arg(x.detach())
+        th = None if theta is None else theta.detach().to(torch.float32).contiguous()
+        out = torch.empty((B, 4, H, W), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.mgr_render_forward(_ptr(xk), strides, _ptr(th), _ptr(out), B, L, H, W, _DTYPES[x.dtype],
+                                        _RANGES[in_range], _stream_ptr(x.device))
+        _lib.check(rc, "mgr_render_forward")
+        _lib.launch_count += 1
+        ctx.in_range = in_range
+        ctx.theta_dtype = None if theta is None else theta.dtype
+        ctx.save_for_backward(xk, th, out)
+        ctx.x_strides = strides
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        xk, th, out = ctx.saved_tensors
+        B, L, _, H, W = xk.shape
+        need_x = ctx.needs_input_grad[0]
+        need_t = th is not None and ctx.needs_input_grad[1]
+        flags = (_lib.MGR_NEED_GRAD_X if need_x else 0) | (_lib.MGR_NEED_GRAD_THETA if need_t else 0)
+        if flags == 0:
+            return None, None, None
+        go = grad_out.to(xk.dtype).contiguous()
+        gx = torch.empty((B, L, 4, H, W), dtype=xk.dtype, device=xk.device) if need_x else None
+        gt = torch.empty((B, L, 2, 3), dtype=torch.float32, device=xk.device) if need_t else None
+        dt = _DTYPES[xk.dtype]
+        ws_bytes = lib.mgr_render_backward_workspace_bytes(B, L, H, W, dt, int(th is not None), flags)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xk.device) if ws_bytes else None
+        with torch.cuda.device(xk.device):
+            rc = lib.mgr_render_backward(_ptr(xk), ctx.x_strides, _ptr(th), _ptr(out), _ptr(go), _ptr(gx), _ptr(gt),
+                                         _ptr(ws), ws_bytes, B, L, H, W, dt, _RANGES[ctx.in_range], flags,
+                                         _stream_ptr(xk.device))
+        _lib.check(rc, "mgr_render_backward")
+        _lib.launch_count += 1
+        if gt is not None and ctx.theta_dtype != torch.float32:
+            gt = gt.to(ctx.theta_dtype)
+        return gx, gt, None
+
+
+def render(x: torch.Tensor, theta: torch.Tensor | None = None, *, in_range: str = "m11") -> torch.Tensor:
+    """Warp every layer of ``x`` [B,L,4,H,W] by ``theta`` [B,L,2,3] (``affine_grid`` +
+    bilinear zero-padded ``grid_sample``, ``align_corners=False``) and alpha-over composite back
+    (layer 0) to front.  Returns [B,4,H,W] straight-alpha RGBA in the same range and dtype as ``x``.
+
+    Differentiable w.r.t. ``x`` and ``theta``.  Where the composited alpha is exactly 0 all
+    gradients are 0 (the reference yields NaN there, ``image_utils.py:128-133``).
+    """
+    _check_inputs(x, theta, in_range)
+    return _Render.apply(x, theta, in_range)
+
+
+def alpha_composite_pytorch(blchw_lchw: torch.Tensor, use_premultiplied: bool = False) -> torch.Tensor:
+    """Drop-in for ``custom_utils.image_utils.alpha_composite_pytorch`` (range [0,1]).
+
+    Only the default ``use_premultiplied=False`` behaviour exists: in the reference the batched
+    premultiplied branch computes and discards its result (``image_utils.py:161-163``), so the
+    default path is what every caller gets.
+    """
+    if use_premultiplied:
+        raise NotImplementedError("use_premultiplied=True is dead code in the reference (image_utils.py:161-163)")
+    if blchw_lchw.dim() == 4:
+        return render(blchw_lchw.unsqueeze(0), None, in_range="01")[0]
+    return render(blchw_lchw, None, in_range="01")

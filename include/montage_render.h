@@ -1,0 +1,104 @@
+/*
+ * montage_render.h -- C ABI of libmontage_render.so (B200 / sm_100a).
+ *
+ * The drop-in boundary for ONE hot path of uchidalab/docker-montage-gan: the global GAN's
+ * analytic renderer = warp every RGBA layer by its 2x3 placement, then alpha-over composite
+ * back to front; forward and backward.  Plain pointers and sizes only: no torch types, no
+ * C++ in the signatures, so the host side can be bound from ctypes / cffi / pybind / cgo.
+ *
+ * Reference interfaces replaced (paths relative to /root/reference/montage_gan):
+ *   - the warp inside STNv2c.forward / STNv2b.forward      fukuwarai/networks.py:247-258, 217-226
+ *     (torch.nn.functional.affine_grid + grid_sample, bilinear, zeros, align_corners=False)
+ *   - alpha_composite_pytorch (default, non-premultiplied)   custom_utils/image_utils.py:112-163
+ *   - normalize_zero1 / normalize_minus11                     custom_utils/image_utils.py:184-195
+ *   - the chain at MontageGANLoss.run_global_D                custom/loss_aio.py:245-257 (:251)
+ *   - the call signature of Renderer*.forward                 diff_rendering/networks.py:36-44
+ *   - convert_translate_to_2x3                                custom_utils/image_utils.py:316-335
+ *   - make_batch_for_pos_estimator (pad to canvas + stack)    custom_utils/image_utils.py:216-243
+ * The reference binds its own native ops with pybind11 torch extensions
+ * (torch_utils/ops/bias_act.cpp:94-97, upfirdn2d.cpp:98-101); INTEGRATION.md shows the ctypes
+ * stub a maintainer adds instead.
+ *
+ * Conventions
+ *   - Tensors: x [B,L,4,H,W] (RGBA, alpha = channel 3), theta [B,L,2,3] float32 mapping OUTPUT
+ *     normalised coords to INPUT normalised coords (align_corners=False), out [B,4,H,W].
+ *   - Layer 0 is the back (image_utils.py:142-146).
+ *   - dtype: element type of x / out / grad_out / grad_x.  All arithmetic is fp32 in registers.
+ *   - range_mode MGR_RANGE_M11: x and out in [-1,1]; the kernel applies the STNv2c "+1 ...
+ *     -1" workaround and normalize_zero1 / normalize_minus11 internally.  MGR_RANGE_01: x and
+ *     out in [0,1] (STNv2b / random_position / bare alpha_composite_pytorch).
+ *   - Where the composited alpha is exactly 0 every gradient is defined as 0 (the reference
+ *     produces NaN there: 0/0 in a_over_b, image_utils.py:128-133).
+ *   - All device pointers belong to the CURRENT CUDA device; every call is asynchronous on
+ *     `stream` (a cudaStream_t passed as void*), never synchronises, never allocates device
+ *     memory, and keeps no pointer after returning: graph-capturable.
+ *   - Return value: 0 on success, otherwise a non-zero code (MGR_ERR_* or a cudaError_t
+ *     offset by MGR_ERR_CUDA_BASE); mgr_last_error() returns a thread-local message.
+ *   - x_strides: element strides of x for [B,L,4,H,W]; NULL means contiguous.  The innermost
+ *     (W) stride must be 1 for the tiled kernels' vector loads; other strides are free
+ *     (e.g. a [B,L*4,H,W] view or a batch slice).
+ */
+#ifndef MONTAGE_RENDER_H_
+#define MONTAGE_RENDER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MGR_ABI_VERSION 1
+
+enum { MGR_F32 = 0, MGR_BF16 = 1, MGR_F16 = 2 };
+enum { MGR_RANGE_M11 = 0, MGR_RANGE_01 = 1 };
+enum { MGR_NEED_GRAD_X = 1, MGR_NEED_GRAD_THETA = 2 };
+enum {
+  MGR_OK = 0,
+  MGR_ERR_INVALID_ARGUMENT = 1,
+  MGR_ERR_UNSUPPORTED = 2,
+  MGR_ERR_WORKSPACE_TOO_SMALL = 3,
+  MGR_ERR_CUDA_BASE = 1000
+};
+
+/* ABI / build identification. */
+int mgr_abi_version(void);
+const char* mgr_build_info(void);
+/* Thread-local, NUL-terminated description of the last non-zero return on this thread. */
+const char* mgr_last_error(void);
+
+/*
+ * Fused warp + composite, forward.
+ *   replaces: fukuwarai/networks.py:250-257 + custom/loss_aio.py:251 (theta != NULL)
+ *             custom/loss_aio.py:251 alone on the real branch :313-320 (theta == NULL)
+ * out is written completely.
+ */
+int mgr_render_forward(const void* x, const int64_t* x_strides, const float* theta, void* out,
+                       int B, int L, int H, int W, int dtype, int range_mode, void* stream);
+
+/*
+ * Bytes of scratch mgr_render_backward needs for this problem (0 is possible).
+ */
+size_t mgr_render_backward_workspace_bytes(int B, int L, int H, int W, int dtype, int has_theta,
+                                           int flags);
+
+/*
+ * Fused warp + composite, backward (the autograd of the chain above).
+ *   out       saved forward result [B,4,H,W] (same dtype), read-only
+ *   grad_out  [B,4,H,W] contiguous
+ *   grad_x    [B,L,4,H,W] contiguous, written completely (no pre-zeroing needed); may be NULL
+ *             when flags lacks MGR_NEED_GRAD_X
+ *   grad_theta[B,L,2,3] float32, written completely; may be NULL when theta is NULL or flags
+ *             lacks MGR_NEED_GRAD_THETA
+ *   workspace device scratch of at least mgr_render_backward_workspace_bytes(...) bytes,
+ *             256-byte aligned; contents undefined on entry and exit
+ */
+int mgr_render_backward(const void* x, const int64_t* x_strides, const float* theta,
+                        const void* out, const void* grad_out, void* grad_x, float* grad_theta,
+                        void* workspace, size_t workspace_bytes, int B, int L, int H, int W,
+                        int dtype, int range_mode, int flags, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MONTAGE_RENDER_H_ */

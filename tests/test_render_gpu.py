@@ -1,0 +1,226 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the oracle and the golden vectors
+generated from the real reference.  Tolerances are the north-star's: forward 1e-5 max-abs,
+gradients 1e-4 relative to max|ref| (fp32), judged three-way (helpers.three_way)."""
+import numpy as np
+import pytest
+import torch
+
+import montage_gan_b200  # noqa: F401
+from montage_gan_b200 import render as mr, synth
+from oracle import restatement as R
+from oracle import torch_chain as TC
+from helpers import FWD_TOL, GRAD_TOL, max_abs, rel_err, three_way
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _run_cuda(x, theta, go, in_range="m11", dtype=torch.float32):
+    xd = x.to(DEV, dtype).requires_grad_(True)
+    td = None if theta is None else theta.to(DEV).requires_grad_(True)
+    out = mr.render(xd, td, in_range=in_range)
+    out.backward(go.to(DEV, dtype))
+    torch.cuda.synchronize()
+    return dict(out=out.detach().float().cpu().numpy(), grad_x=xd.grad.float().cpu().numpy(),
+                grad_theta=None if td is None else td.grad.cpu().numpy())
+
+
+def _assert_three_way(new, r32, r64, what):
+    ok, rep = three_way(new["out"], r32["out"], r64["out"], FWD_TOL, max_abs)
+    assert ok, (what, "out", rep)
+    ok, rep = three_way(new["grad_x"], r32["grad_x"], r64["grad_x"], GRAD_TOL, rel_err)
+    assert ok, (what, "grad_x", rep)
+    if new["grad_theta"] is not None and np.isfinite(np.asarray(r64["grad_theta"])).all():
+        ok, rep = three_way(new["grad_theta"], r32["grad_theta"], r64["grad_theta"], GRAD_TOL, rel_err)
+        assert ok, (what, "grad_theta", rep)
+
+
+def test_golden_vectors(golden):
+    """Every golden case produced by the real reference: forward, grad_x, grad_theta."""
+    for name in golden["cases"]:
+        x = torch.from_numpy(golden[f"{name}/x"])
+        theta = torch.from_numpy(golden[f"{name}/theta"]) if f"{name}/theta" in golden.files else None
+        go = torch.from_numpy(golden[f"{name}/grad_out"])
+        in_range = str(golden[f"{name}/in_range"])
+        new = _run_cuda(x, theta, go, in_range)
+        r32 = {k: golden[f"{name}/ref32/{k}"] for k in ("out", "grad_x")}
+        r64 = {k: golden[f"{name}/ref64/{k}"] for k in ("out", "grad_x")}
+        for r, tag in ((r32, "ref32"), (r64, "ref64")):
+            r["grad_theta"] = golden[f"{name}/{tag}/grad_theta"] if theta is not None else None
+        _assert_three_way(new, r32, r64, name)
+        # where the reference is NaN (transparent back layers) we must be finite, and exactly the
+        # closed-form value -- which the fp64 restatement provides
+        rr = R.render_fwd_bwd(x.numpy(), None if theta is None else theta.numpy(), go.numpy(), in_range, np.float64)
+        assert np.isfinite(new["grad_x"]).all(), name
+        assert rel_err(new["grad_x"], rr["grad_x"]) < GRAD_TOL, name
+        zero_cov = np.broadcast_to(rr["nan_mask"][:, None, None], new["grad_x"].shape)
+        assert np.all(new["grad_x"][zero_cov] == 0), name
+
+
+def test_known_answers(golden):
+    out = mr.alpha_composite_pytorch(torch.from_numpy(golden["ka/order/in"]).to(DEV)).cpu().numpy()
+    assert np.array_equal(out, golden["ka/order/out"])
+    out = mr.alpha_composite_pytorch(torch.from_numpy(golden["ka/transparent/in"]).to(DEV)).cpu().numpy()
+    assert not out.any()
+    out = mr.alpha_composite_pytorch(torch.from_numpy(golden["ka/half/in"]).to(DEV)).cpu().numpy()
+    assert max_abs(out, golden["ka/half/out"]) < 1e-6
+    # unbatched [L,4,H,W] input, like the reference accepts
+    out = mr.alpha_composite_pytorch(torch.from_numpy(golden["ka/half/in"][0]).to(DEV)).cpu().numpy()
+    assert max_abs(out, golden["ka/half/out"][0]) < 1e-6
+
+
+@pytest.mark.parametrize("lf,tf", [("W", "I"), ("S", "I"), ("S", "T"), ("W", "T"), ("W", "X"), ("F", "I")])
+@pytest.mark.parametrize("go_kind", ["ones", "randn"])
+def test_parity_seeded(lf, tf, go_kind):
+    B, L, H, W = 3, 7, 64, 48
+    x = synth.make_layers(B, L, H, W, lf, seed=11)
+    th = synth.make_theta(B, L, tf, seed=11)
+    go = synth.make_grad_out(B, H, W, go_kind, seed=11)
+    new = _run_cuda(x, th, go)
+    r32 = R.render_fwd_bwd(x.numpy(), th.numpy(), go.numpy(), "m11", np.float32)
+    r64 = R.render_fwd_bwd(x.numpy(), th.numpy(), go.numpy(), "m11", np.float64)
+    _assert_three_way(new, r32, r64, (lf, tf, go_kind))
+
+
+def test_parity_config1_vs_reference_chain():
+    """BASELINE config 1 (B=8, L=7, 256x256, fp32, random affine): the CUDA path against the
+    reference chain itself (torch port == reference bitwise, tests/test_oracle.py) in fp32 and fp64."""
+    B, L, H, W = 8, 7, 256, 256
+    x = synth.make_layers(B, L, H, W, "S", seed=0)
+    th = synth.make_theta(B, L, "I", seed=0)
+    go = synth.make_grad_out(B, H, W, "randn", seed=0)
+    new = _run_cuda(x, th, go)
+    r32 = {k: (None if v is None else v.numpy()) for k, v in TC.fwd_bwd(TC.port_chain, x, th, go, "m11", torch.float32).items()}
+    r64 = {k: (None if v is None else v.numpy()) for k, v in TC.fwd_bwd(TC.port_chain, x, th, go, "m11", torch.float64).items()}
+    _assert_three_way(new, r32, r64, "config1")
+    # and we are much closer to fp64 truth than the tolerance
+    assert max_abs(new["out"], r64["out"]) < FWD_TOL
+    assert rel_err(new["grad_x"], r64["grad_x"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("shape", [(1, 1, 5, 7), (2, 3, 1, 1), (1, 2, 33, 257), (2, 9, 40, 24), (1, 32, 16, 16)])
+def test_ragged_shapes(shape):
+    B, L, H, W = shape
+    x = synth.make_layers(B, L, H, W, "W", seed=5)
+    th = synth.make_theta(B, L, "I", seed=5)
+    go = synth.make_grad_out(B, H, W, "randn", seed=5)
+    new = _run_cuda(x, th, go)
+    r64 = R.render_fwd_bwd(x.numpy(), th.numpy(), go.numpy(), "m11", np.float64)
+    assert max_abs(new["out"], r64["out"]) < FWD_TOL
+    assert rel_err(new["grad_x"], r64["grad_x"]) < GRAD_TOL
+    assert rel_err(new["grad_theta"], r64["grad_theta"]) < 5e-4
+
+
+@pytest.mark.parametrize("in_range", ["m11", "01"])
+def test_composite_only(in_range):
+    B, L, H, W = 2, 9, 40, 56
+    x = synth.make_layers(B, L, H, W, "F", seed=9)
+    if in_range == "01":
+        x = (x + 1) / 2
+    go = synth.make_grad_out(B, H, W, "randn", seed=9)
+    new = _run_cuda(x, None, go, in_range)
+    r64 = R.render_fwd_bwd(x.numpy(), None, go.numpy(), in_range, np.float64)
+    assert max_abs(new["out"], r64["out"]) < FWD_TOL
+    assert rel_err(new["grad_x"], r64["grad_x"]) < GRAD_TOL
+    assert np.isfinite(new["grad_x"]).all()
+
+
+def test_strided_input_views():
+    """x as a batch slice and as a channel-padded view: strides go through the ABI untouched."""
+    B, L, H, W = 4, 5, 24, 32
+    big = synth.make_layers(B + 2, L, H, W + 8, "W", seed=2).to(DEV)
+    x = big[1:B + 1, :, :, :, 3:W + 3]
+    assert not x.is_contiguous()
+    th = synth.make_theta(B, L, "I", seed=2).to(DEV)
+    a = mr.render(x, th)
+    b = mr.render(x.contiguous(), th)
+    assert torch.equal(a, b)
+    xs = x.detach().requires_grad_(True)
+    xc = x.detach().contiguous().requires_grad_(True)
+    go = synth.make_grad_out(B, H, W, seed=2).to(DEV)
+    mr.render(xs, th).backward(go)
+    mr.render(xc, th).backward(go)
+    assert rel_err(xs.grad.cpu().numpy(), xc.grad.cpu().numpy()) < 1e-6
+
+
+def test_needs_input_grad_subsets():
+    B, L, H, W = 2, 4, 16, 16
+    x = synth.make_layers(B, L, H, W, "W", seed=1).to(DEV)
+    th = synth.make_theta(B, L, "I", seed=1).to(DEV)
+    go = synth.make_grad_out(B, H, W, seed=1).to(DEV)
+    xa, ta = x.clone().requires_grad_(True), th.clone().requires_grad_(True)
+    mr.render(xa, ta).backward(go)
+    xb = x.clone().requires_grad_(True)
+    mr.render(xb, th).backward(go)
+    tb = th.clone().requires_grad_(True)
+    mr.render(x, tb).backward(go)
+    assert rel_err(xb.grad.cpu().numpy(), xa.grad.cpu().numpy()) < 1e-6
+    assert rel_err(tb.grad.cpu().numpy(), ta.grad.cpu().numpy()) < 1e-5
+    # retain_graph + second backward (custom/loss_aio.py:297-298)
+    xc, tc = x.clone().requires_grad_(True), th.clone().requires_grad_(True)
+    out = mr.render(xc, tc)
+    out.backward(go, retain_graph=True)
+    g1 = tc.grad.clone()
+    out.backward(go)
+    assert rel_err((tc.grad - g1).cpu().numpy(), g1.cpu().numpy()) < 1e-5
+
+
+def test_bf16_storage():
+    """bf16 I/O, fp32 math: compare with the fp64 oracle evaluated on the bf16-rounded inputs."""
+    B, L, H, W = 2, 7, 64, 64
+    x = synth.make_layers(B, L, H, W, "S", seed=4).to(torch.bfloat16)
+    th = synth.make_theta(B, L, "I", seed=4)
+    go = synth.make_grad_out(B, H, W, seed=4).to(torch.bfloat16)
+    new = _run_cuda(x, th, go, dtype=torch.bfloat16)
+    r64 = R.render_fwd_bwd(x.float().numpy(), th.numpy(), go.float().numpy(), "m11", np.float64)
+    assert max_abs(new["out"], r64["out"]) < 2 ** -7          # bf16 rounding of values in [-1,1]
+    assert rel_err(new["grad_x"], r64["grad_x"]) < 2 ** -7
+    assert rel_err(new["grad_theta"], r64["grad_theta"]) < 2e-2   # saved `out` is bf16 (o_rgb in G_A)
+
+
+def test_overshoot_and_nan_free():
+    """Generator overshoot: values outside [-1,1] are not clamped (training_loop_aio.py:753)."""
+    B, L, H, W = 2, 5, 32, 32
+    x = synth.make_layers(B, L, H, W, "W", seed=6) * 1.2
+    th = synth.make_theta(B, L, "I", seed=6)
+    go = synth.make_grad_out(B, H, W, seed=6)
+    new = _run_cuda(x, th, go)
+    r64 = R.render_fwd_bwd(x.numpy(), th.numpy(), go.numpy(), "m11", np.float64)
+    scale = max(1.0, float(np.abs(r64["out"]).max()))
+    assert max_abs(new["out"], r64["out"]) < 1e-4 * scale
+    assert np.isfinite(new["grad_x"]).all() and np.isfinite(new["grad_theta"]).all()
+
+
+def test_full_size_properties_config2():
+    """BASELINE config 2 shape (B=64, L=7, 256x256): size-independent properties.
+    (1) linearity of the backward in grad_out; (2) an opaque front layer hides everything behind
+    it (grad of hidden layers is exactly 0 under identity theta); (3) batch-shard invariance."""
+    B, L, H, W = 64, 7, 256, 256
+    x = synth.make_layers(B, L, H, W, "S", seed=21).to(DEV)
+    th = synth.make_theta(B, L, "I", seed=21).to(DEV)
+    g1 = synth.make_grad_out(B, H, W, seed=1).to(DEV)
+    g2 = synth.make_grad_out(B, H, W, seed=2).to(DEV)
+
+    def grads(go):
+        xx, tt = x.clone().requires_grad_(True), th.clone().requires_grad_(True)
+        out = mr.render(xx, tt)
+        out.backward(go)
+        return out.detach(), xx.grad, tt.grad
+    o1, gx1, gt1 = grads(g1)
+    _, gx2, gt2 = grads(g2)
+    _, gx3, gt3 = grads(2 * g1 - 3 * g2)
+    assert rel_err((2 * gx1 - 3 * gx2).cpu().numpy(), gx3.cpu().numpy()) < 1e-5
+    assert rel_err((2 * gt1 - 3 * gt2).cpu().numpy(), gt3.cpu().numpy()) < 1e-3
+    # shard invariance (what multi-GPU batch sharding relies on)
+    o_half = mr.render(x[B // 2:], th[B // 2:])
+    assert torch.equal(o_half, o1[B // 2:])
+    # opaque front layer under identity placement hides the rest
+    xo = x.clone()
+    xo[:, L - 1, 3] = 1.0
+    tho = th.clone()
+    tho[:, L - 1] = torch.eye(2, 3, device=DEV)
+    xo.requires_grad_(True)
+    out = mr.render(xo, tho)
+    out.backward(g1)
+    assert xo.grad[:, :L - 1].abs().max().item() == 0.0
+    assert (out[:, 3] == 1).all()
