@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the analytic renderer (warp + alpha-over, fwd+bwd).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload c2|c1|c3]
+
+Metric (BASELINE.json): composited layer-Mpix/s, fwd+bwd = B*L*H*W / 1e6 / t(fwd+bwd).
+One "step" = one forward + one backward of the render path over one batch of synthetic layer
+stacks.  At N>1 every rank renders its own batch shard (weak scaling, no data-path collective;
+SURVEY.md 8e) and the value is sum(units)/max(time).  Prints ONE JSON line on rank 0.
+
+Arms:
+  default           the CUDA path through the C ABI; `value` with inputs resident in HBM,
+                    `e2e` with pinned HOST buffers and H2D/D2H copies inside the timed region.
+  --impl reference  the reference's own CPU implementation of the path (the torch port of the
+                    reference chain in oracle/torch_chain.py -- /root/reference does not exist on
+                    the GPU box) on all host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (B per GPU, L, H, W, storage dtype, description)
+    "c1": (8, 7, 256, 256, "float32", "C1: B=8 L=7 256x256 RGBA layers, fp32 storage"),
+    "c2": (64, 7, 256, 256, "bfloat16", "C2: B=64 L=7 256x256 RGBA layers, bf16 storage"),
+    "c3": (32, 16, 512, 512, "float32", "C3 shard: B=32 (256/8) L=16 512x512 RGBA layers, fp32 storage"),
+}
+METRIC = "composited layer-Mpix/s fwd+bwd"
+UNIT = "layer-Mpix/s"
+
+
+def algorithmic_bytes(B, L, H, W, s_x, s_o, s_g):
+    """SURVEY.md 8d / BASELINE.md 3: every tensor touched once in its storage dtype."""
+    fwd = B * L * 4 * H * W * s_x + B * 4 * H * W * s_o + 24 * B * L
+    bwd = B * 4 * H * W * s_o + B * L * 4 * H * W * s_x + B * L * 4 * H * W * s_g + 48 * B * L
+    return fwd, bwd
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Polls SM clock and throttle reasons through NVML while the timed region runs."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost"}
+
+    def __init__(self, index):
+        self.samples, self.mask, self.max_mhz, self._stop = [], 0, None, threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:  # noqa: BLE001
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        while not self._stop.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:  # noqa: BLE001
+                try:
+                    self.mask |= int(self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                except Exception:  # noqa: BLE001
+                    pass
+            time.sleep(0.005)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.nv:
+            self.t.join()
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": [n for b, n in self.REASONS.items() if self.mask & b], "samples": len(s)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of the reference chain) -- the only place bench.py executes oracle/
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_throughput(L, H, W, sample_B, min_seconds, max_iters, seed=0):
+    import torch
+    import montage_gan_b200  # noqa: F401
+    from montage_gan_b200 import synth
+    from oracle import torch_chain as TC
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    x = synth.make_layers(sample_B, L, H, W, "S", seed=seed)
+    th = synth.make_theta(sample_B, L, "I", seed=seed)
+    go = synth.make_grad_out(sample_B, H, W, seed=seed)
+    TC.fwd_bwd(TC.port_chain, x, th, go, "m11", torch.float32)          # warm-up
+    times = []
+    t_start = time.perf_counter()
+    while len(times) < max_iters and (len(times) < 3 or time.perf_counter() - t_start < min_seconds):
+        t0 = time.perf_counter()
+        TC.fwd_bwd(TC.port_chain, x, th, go, "m11", torch.float32)
+        times.append(time.perf_counter() - t0)
+    times.sort()
+    med = times[len(times) // 2]
+    return {"value": sample_B * L * H * W / 1e6 / med, "unit": UNIT, "cores": torch.get_num_threads(),
+            "kind": "port",
+            "sample": f"B={sample_B} of the workload (L={L}, {H}x{W}, fp32 as the reference computes), "
+                      f"{len(times)} iterations, median {med * 1e3:.1f} ms; torch {torch.__version__} CPU ATen "
+                      f"affine_grid+grid_sample + per-sample/per-layer Python over loops + autograd backward"}, times
+
+
+def run_reference_arm(args, wl):
+    B, L, H, W, dtype_name, desc = wl
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample_B = min(B, 8)
+    t0 = time.perf_counter()
+    base, times = cpu_reference_throughput(L, H, W, sample_B, min_seconds=0.0, max_iters=args.steps + args.warmup)
+    times = times[-args.steps:] if len(times) > args.steps else times
+    ms = 1e3 * sum(times) / len(times)
+    value = sample_B * L * H * W / 1e6 / (ms / 1e3)
+    base["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": desc + f"; CPU arm runs a B={sample_B} sample per step in fp32",
+                       "theta": "I + 0.25*N(0,1), covering back layer", "layers": "smooth (S) family"},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# CUDA arm
+# ------------------------------------------------------------------------------------------------
+def run_cuda_arm(args, wl):
+    import ctypes
+    import torch
+    import torch.distributed as dist
+    import montage_gan_b200  # noqa: F401
+    from montage_gan_b200 import _lib, render as mr, synth
+
+    B, L, H, W, dtype_name, desc = wl
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    dtype = getattr(torch, dtype_name)
+    dt_code = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}[dtype]
+    es = torch.empty((), dtype=dtype).element_size()
+
+    # ---- synthetic inputs: NSETS rotating sets so no step finds its inputs in L2 -----------------
+    NSETS = 3
+    gen_B = min(B, 16)                      # generate a seeded block on the CPU and tile it
+    xs, ths, gos = [], [], []
+    for k in range(NSETS):
+        seed = 1000 * rank + k
+        xb = synth.make_layers(gen_B, L, H, W, "S", seed=seed)
+        reps = (B + gen_B - 1) // gen_B
+        x = xb.repeat(reps, 1, 1, 1, 1)[:B].to(dev, dtype)
+        # decorrelate the tiled copies with a per-sample roll so samples differ
+        for r in range(1, reps):
+            x[r * gen_B:(r + 1) * gen_B] = torch.roll(x[r * gen_B:(r + 1) * gen_B], shifts=(7 * r, 13 * r), dims=(-2, -1))
+        xs.append(x.contiguous())
+        ths.append(synth.make_theta(B, L, "I", seed=seed).to(dev))
+        gos.append(synth.make_grad_out(B, H, W, "randn", seed=seed).to(dev, dtype))
+    out = torch.empty((B, 4, H, W), dtype=dtype, device=dev)
+    gx = torch.empty((B, L, 4, H, W), dtype=dtype, device=dev)
+    gt = torch.empty((B, L, 2, 3), dtype=torch.float32, device=dev)
+    flags = 3
+    ws_bytes = lib.mgr_render_backward_workspace_bytes(B, L, H, W, dt_code, 1, flags)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    sp = ctypes.c_void_p(stream.cuda_stream)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+
+    def fwd(k):
+        _lib.check(lib.mgr_render_forward(P(xs[k]), None, P(ths[k]), P(out), B, L, H, W, dt_code, 0, sp), "forward")
+
+    def bwd(k):
+        _lib.check(lib.mgr_render_backward(P(xs[k]), None, P(ths[k]), P(out), P(gos[k]), P(gx), P(gt), P(ws),
+                                           ws_bytes, B, L, H, W, dt_code, 0, flags, sp), "backward")
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident timing -----------------------------------------------------------------
+    for i in range(max(args.warmup, 3)):
+        fwd(i % NSETS); bwd(i % NSETS)
+    barrier()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    launches0 = lib.mgr_kernel_launch_count()
+    with ClockSampler(local_rank) as clocks:
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            k = i % NSETS
+            ev[i][0].record(stream); fwd(k)
+            ev[i][1].record(stream); bwd(k)
+            ev[i][2].record(stream)
+        end_ev = torch.cuda.Event(enable_timing=True)
+        end_ev.record(stream)
+        torch.cuda.synchronize(dev)
+        t_wall = time.perf_counter() - t_wall0
+    launches = lib.mgr_kernel_launch_count() - launches0
+    total_ms = ev[0][0].elapsed_time(end_ev)
+    fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
+    bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    barrier()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    max_ms = float(t.item())
+    units_per_step = B * L * H * W            # per rank
+    value = world * units_per_step * args.steps / 1e6 / (max_ms / 1e3)
+
+    # ---- end to end through the public API with pinned host buffers -------------------------------
+    hx = [x.cpu().pin_memory() for x in xs[:2]]
+    hth = [t_.cpu().pin_memory() for t_ in ths[:2]]
+    hgo = [g_.cpu().pin_memory() for g_ in gos[:2]]
+    h_out = torch.empty((B, 4, H, W), dtype=dtype).pin_memory()
+    h_gx = torch.empty((B, L, 4, H, W), dtype=dtype).pin_memory()
+    h_gt = torch.empty((B, L, 2, 3), dtype=torch.float32).pin_memory()
+    h2d = hx[0].numel() * es + hth[0].numel() * 4 + hgo[0].numel() * es
+    d2h = h_out.numel() * es + h_gx.numel() * es + h_gt.numel() * 4
+
+    def e2e_step(k):
+        xd = hx[k].to(dev, non_blocking=True).requires_grad_(True)
+        td = hth[k].to(dev, non_blocking=True).requires_grad_(True)
+        god = hgo[k].to(dev, non_blocking=True)
+        o = mr.render(xd, td)
+        o.backward(god)
+        h_out.copy_(o.detach(), non_blocking=True)
+        h_gx.copy_(xd.grad, non_blocking=True)
+        h_gt.copy_(td.grad, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()      # the step's results are on the host
+
+    e2e_steps = 0 if args.kernels_only else max(3, min(args.steps, 10))
+    for i in range(2 if e2e_steps else 0):
+        e2e_step(i % 2)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for i in range(e2e_steps):
+        e2e_step(i % 2)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * units_per_step * e2e_steps / 1e6 / (float(te.item()) / 1e3) if e2e_steps else None
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        fb, bb = algorithmic_bytes(B, L, H, W, es, es, es)
+        # dominant kernel = the backward pass (scatter + theta reduction)
+        achieved = bb / 1e9 / (bwd_ms / 1e3)
+        roofline = {"bound": "hbm", "kernel": "render backward (mgr_render_backward)", "achieved": achieved,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "algorithmic_bytes_per_launch": bb,
+                    "forward": {"achieved": fb / 1e9 / (fwd_ms / 1e3), "frac": fb / 1e9 / (fwd_ms / 1e3) / peak,
+                                "ms": fwd_ms, "algorithmic_bytes_per_launch": fb},
+                    "backward_ms": bwd_ms,
+                    "fwd_bwd": {"achieved": (fb + bb) / 1e9 / ((fwd_ms + bwd_ms) / 1e3),
+                                "frac": (fb + bb) / 1e9 / ((fwd_ms + bwd_ms) / 1e3) / peak,
+                                "frac_of_nominal_8TBs": (fb + bb) / 1e9 / ((fwd_ms + bwd_ms) / 1e3) / 8000.0}}
+        cpu_base = None
+        if not args.kernels_only:
+            cpu_base, _ = cpu_reference_throughput(L, H, W, min(B, 8), min_seconds=args.cpu_seconds, max_iters=50)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": max_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": desc + " per GPU, fp32 arithmetic in registers",
+                           "theta": "I + 0.25*N(0,1), covering back layer", "layers": "smooth (S) family",
+                           "l2": f"{NSETS} rotating input sets of {xs[0].numel() * es / 1e6:.0f} MB each (> 126 MB L2)",
+                           "sharding": f"batch-sharded, {B} samples per GPU, no data-path collective"},
+                "roofline": roofline, "cpu_baseline": cpu_base,
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                        "steps": e2e_steps, "api": "montage_gan_b200.render.render + autograd, pinned host buffers"},
+                "gpu_launches": int(launches), "clocks": clocks.summary(),
+                "wall_s_timed_region": t_wall}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline sampling budget")
+    ap.add_argument("--kernels-only", action="store_true",
+                    help="skip the e2e and cpu_baseline legs (for ncu captures; not a valid bench line)")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, wl)
+    else:
+        run_cuda_arm(args, wl)
+
+
+if __name__ == "__main__":
+    main()

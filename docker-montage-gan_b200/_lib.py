@@ -30,6 +30,7 @@ SYMBOLS = {
     "mgr_abi_version": (_i, []),
     "mgr_build_info": (_c.c_char_p, []),
     "mgr_last_error": (_c.c_char_p, []),
+    "mgr_kernel_launch_count": (_c.c_longlong, []),
     "mgr_render_forward": (_i, [_vp, _i64p, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mgr_render_backward_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "mgr_render_backward": (_i, [_vp, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -14,6 +14,7 @@ int launch_forward(const void* x, const float* theta, void* out, const mgr::Geom
   else
     mgr::render_fwd_direct<T, false><<<grid, mgr::kDirectThreads, 0, s>>>((const T*)x, nullptr, (T*)out, g);
   MGR_CUDA(cudaGetLastError());
+  count_launch();
   return MGR_OK;
 }
 
@@ -31,6 +32,7 @@ int launch_backward_l(const void* x, const float* theta, const void* out, const 
   else if (nt) MGR_LAUNCH(false, true);
 #undef MGR_LAUNCH
   MGR_CUDA(cudaGetLastError());
+  count_launch();
   return MGR_OK;
 }
 
@@ -59,6 +61,7 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
       const long long blocks = (n + threads - 1) / threads;
       mgr::cast_from_f32<T><<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), threads, 0, s>>>(gx32, (T*)gx, n);
       MGR_CUDA(cudaGetLastError());
+      count_launch();
     }
     return MGR_OK;
   }

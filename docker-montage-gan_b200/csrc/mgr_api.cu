@@ -3,6 +3,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 
 #include "montage_render.h"
 #include "mgr_common.cuh"
@@ -12,6 +13,7 @@
 
 namespace {
 thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
 }
 
 namespace mgr {
@@ -26,6 +28,7 @@ int fail(int code, const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
   return fail(MGR_ERR_CUDA_BASE + (int)e, "%s: %s", what, cudaGetErrorString(e));
 }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 }  // namespace mgr
 
 namespace {
@@ -69,6 +72,8 @@ const char* mgr_build_info(void) {
 }
 
 const char* mgr_last_error(void) { return g_err; }
+
+long long mgr_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int mgr_render_forward(const void* x, const int64_t* x_strides, const float* theta, void* out, int B, int L, int H,
                        int W, int dtype, int range_mode, void* stream) {

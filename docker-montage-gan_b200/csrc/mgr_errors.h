@@ -6,6 +6,7 @@
 namespace mgr {
 int fail(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+void count_launch(int n = 1);   // process-wide count of kernels launched by this library
 }  // namespace mgr
 
 #define MGR_CUDA(expr)                                        \

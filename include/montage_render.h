@@ -66,6 +66,9 @@ int mgr_abi_version(void);
 const char* mgr_build_info(void);
 /* Thread-local, NUL-terminated description of the last non-zero return on this thread. */
 const char* mgr_last_error(void);
+/* Number of CUDA kernels this library has launched in this process (all threads, all calls);
+ * bench.py differences it around the timed region to report "gpu_launches". */
+long long mgr_kernel_launch_count(void);
 
 /*
  * Fused warp + composite, forward.

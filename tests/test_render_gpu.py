@@ -53,8 +53,9 @@ def test_golden_vectors(golden):
         rr = R.render_fwd_bwd(x.numpy(), None if theta is None else theta.numpy(), go.numpy(), in_range, np.float64)
         assert np.isfinite(new["grad_x"]).all(), name
         assert rel_err(new["grad_x"], rr["grad_x"]) < GRAD_TOL, name
-        zero_cov = np.broadcast_to(rr["nan_mask"][:, None, None], new["grad_x"].shape)
-        assert np.all(new["grad_x"][zero_cov] == 0), name
+        if theta is None:       # output pixel == source texel only without a warp
+            zero_cov = np.broadcast_to(rr["nan_mask"][:, None, None], new["grad_x"].shape)
+            assert np.all(new["grad_x"][zero_cov] == 0), name
 
 
 def test_known_answers(golden):
