@@ -197,15 +197,16 @@ def run_cuda_arm(args, wl):
     flags = 3
     ws_bytes = lib.mgr_render_backward_workspace_bytes(B, L, H, W, dt_code, 1, flags)
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    sav = torch.empty(max(lib.mgr_saved_alpha_bytes(B, L, H, W, dt_code), 1), dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream(dev)
     sp = ctypes.c_void_p(stream.cuda_stream)
     P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
 
     def fwd(k):
-        _lib.check(lib.mgr_render_forward(P(xs[k]), None, P(ths[k]), P(out), B, L, H, W, dt_code, 0, sp), "forward")
+        _lib.check(lib.mgr_render_forward(P(xs[k]), None, P(ths[k]), P(out), P(sav), B, L, H, W, dt_code, 0, sp), "forward")
 
     def bwd(k):
-        _lib.check(lib.mgr_render_backward(P(xs[k]), None, P(ths[k]), P(out), P(gos[k]), P(gx), P(gt), P(ws),
+        _lib.check(lib.mgr_render_backward(P(xs[k]), None, P(ths[k]), P(out), P(gos[k]), P(sav), P(gx), P(gt), P(ws),
                                            ws_bytes, B, L, H, W, dt_code, 0, flags, sp), "backward")
 
     def barrier():

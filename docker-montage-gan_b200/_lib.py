@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libmontage_render.so")
 MGR_F32, MGR_BF16, MGR_F16 = 0, 1, 2
 MGR_RANGE_M11, MGR_RANGE_01 = 0, 1
 MGR_NEED_GRAD_X, MGR_NEED_GRAD_THETA = 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _c = ctypes
 _vp, _i, _sz = _c.c_void_p, _c.c_int, _c.c_size_t
@@ -31,9 +31,11 @@ SYMBOLS = {
     "mgr_build_info": (_c.c_char_p, []),
     "mgr_last_error": (_c.c_char_p, []),
     "mgr_kernel_launch_count": (_c.c_longlong, []),
-    "mgr_render_forward": (_i, [_vp, _i64p, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "mgr_set_debug_path": (_i, [_i]),
+    "mgr_saved_alpha_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "mgr_render_forward": (_i, [_vp, _i64p, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mgr_render_backward_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
-    "mgr_render_backward": (_i, [_vp, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "mgr_render_backward": (_i, [_vp, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp]),
 }
 
 _lock = threading.Lock()

@@ -2,11 +2,42 @@
 #pragma once
 #include "mgr_errors.h"
 #include "render_direct.cuh"
+#include "render_bwd_tiled.cuh"
+#include "render_tiled.cuh"
 
 namespace mgr {
 
+// The tiled kernels stage footprints with 128-bit vector loads (4 fp32 / 8 16-bit texels): every
+// plane row must start on a vector boundary and W must be a multiple of the vector width (a lane's
+// texels are then all inside or all outside the image).
 template <typename T>
-int launch_forward(const void* x, const float* theta, void* out, const mgr::Geometry& g, cudaStream_t s) {
+bool tiled_ok(const void* x, const Geometry& g) {
+  if (debug_path() == 1) return false;
+  const int v = kStageVec;
+  const long long layer_bytes = (3 * g.sc + (long long)g.H * g.sh) * (long long)sizeof(T);   // 32-bit offsets inside a layer
+  return (g.W % v == 0) && (g.sh % v == 0) && (g.sc % v == 0) && (g.sl % v == 0) && (g.sb % v == 0) &&
+         (reinterpret_cast<uintptr_t>(x) % (kStageVec * sizeof(T)) == 0) && g.sc >= 0 && (long long)g.H * g.W < (1LL << 29) && layer_bytes < (1LL << 31);
+}
+
+template <typename T>
+int launch_forward(const void* x, const float* theta, void* out, void* sav, const mgr::Geometry& g, cudaStream_t s) {
+  if (theta && g.L >= 2 && tiled_ok<T>(x, g)) {
+    using Vec = typename Texel<T>::Vec;
+    const size_t smem = tiled_smem_bytes(g.L, sizeof(Vec));
+    static bool configured = false;   // per dtype instantiation; attribute is sticky per function
+    if (!configured) {
+      MGR_CUDA(cudaFuncSetAttribute(render_fwd_tiled<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      MGR_CUDA(cudaFuncSetAttribute(render_fwd_tiled<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      configured = true;
+    }
+    dim3 grid((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B);
+    using SA = typename SavedAlpha<T>::type;
+    if (sav) render_fwd_tiled<T, true><<<grid, kTiledThreads, smem, s>>>((const T*)x, theta, (T*)out, (SA*)sav, g);
+    else render_fwd_tiled<T, false><<<grid, kTiledThreads, smem, s>>>((const T*)x, theta, (T*)out, nullptr, g);
+    MGR_CUDA(cudaGetLastError());
+    count_launch();
+    return MGR_OK;
+  }
   dim3 grid((g.W + mgr::kTileW - 1) / mgr::kTileW, (g.H + mgr::kTileH - 1) / mgr::kTileH, g.B);
   const size_t smem = sizeof(mgr::TileAffine) * g.L;
   if (theta)
@@ -44,9 +75,41 @@ int launch_backward(const void* x, const float* theta, const void* out, const vo
 }
 
 template <typename T>
-int backward_typed(const void* x, const float* theta, const void* out, const void* gout, void* gx, float* gtheta,
-                   void* ws, const mgr::Geometry& g, int flags, cudaStream_t s) {
+int backward_typed(const void* x, const float* theta, const void* out, const void* gout, const void* sav, void* gx,
+                   float* gtheta, void* ws, const mgr::Geometry& g, int flags, cudaStream_t s) {
   const long long n = (long long)g.B * g.L * 4 * g.H * g.W;
+  if (theta && sav && g.L >= 2 && tiled_ok<T>(x, g)) {
+    // two-pass tiled backward: records in the workspace, no atomics on grad_x
+    using Vec = typename Texel<T>::Vec;
+    using SA = typename SavedAlpha<T>::type;
+    const bool nx = flags & MGR_NEED_GRAD_X, nt = flags & MGR_NEED_GRAD_THETA;
+    float2* rec = reinterpret_cast<float2*>(ws);
+    float4* gp = reinterpret_cast<float4*>(reinterpret_cast<char*>(ws) + sizeof(float2) * (size_t)g.B * g.L * g.H * g.W);
+    static bool configured = false;
+    if (!configured) {
+      MGR_CUDA(cudaFuncSetAttribute(render_bwd_pass1<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      MGR_CUDA(cudaFuncSetAttribute(render_bwd_pass1<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      configured = true;
+    }
+    if (nt) MGR_CUDA(cudaMemsetAsync(gtheta, 0, sizeof(float) * 6 * g.B * g.L, s));
+    const size_t smem = tiled_smem_bytes(g.L, sizeof(Vec)) + sizeof(float) * 6 * g.L;
+    dim3 grid((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B);
+    if (nt)
+      render_bwd_pass1<T, true><<<grid, kTiledThreads, smem, s>>>((const T*)x, theta, (const T*)out, (const T*)gout,
+                                                                  (const SA*)sav, rec, gp, gtheta, g);
+    else
+      render_bwd_pass1<T, false><<<grid, kTiledThreads, smem, s>>>((const T*)x, theta, (const T*)out, (const T*)gout,
+                                                                   (const SA*)sav, rec, gp, nullptr, g);
+    MGR_CUDA(cudaGetLastError());
+    count_launch();
+    if (nx) {
+      dim3 grid2((g.W + kP2W - 1) / kP2W, (g.H + kP2H - 1) / kP2H, g.B * g.L);
+      render_bwd_pass2<T><<<grid2, kP2W * kP2H, 0, s>>>(theta, rec, gp, (T*)gx, g);
+      MGR_CUDA(cudaGetLastError());
+      count_launch();
+    }
+    return MGR_OK;
+  }
   if (theta) {
     if (flags & MGR_NEED_GRAD_THETA) MGR_CUDA(cudaMemsetAsync(gtheta, 0, sizeof(float) * 6 * g.B * g.L, s));
     float* gx32 = nullptr;
@@ -68,15 +131,15 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
   return launch_backward<T, false>(x, nullptr, out, gout, nullptr, gx, nullptr, g, flags & MGR_NEED_GRAD_X, s);
 }
 
-
 }  // namespace mgr
 
 #include "launchers_decl.h"
 #define MGR_INSTANTIATE(SUFFIX, T)                                                                           \
-  int mgr_fwd_##SUFFIX(const void* x, const float* theta, void* out, const mgr::Geometry& g, cudaStream_t s) { \
-    return mgr::launch_forward<T>(x, theta, out, g, s);                                                      \
+  int mgr_fwd_##SUFFIX(const void* x, const float* theta, void* out, void* sav, const mgr::Geometry& g,     \
+                       cudaStream_t s) {                                                                     \
+    return mgr::launch_forward<T>(x, theta, out, sav, g, s);                                                 \
   }                                                                                                          \
-  int mgr_bwd_##SUFFIX(const void* x, const float* theta, const void* out, const void* gout, void* gx,       \
-                       float* gtheta, void* ws, const mgr::Geometry& g, int flags, cudaStream_t s) {         \
-    return mgr::backward_typed<T>(x, theta, out, gout, gx, gtheta, ws, g, flags, s);                         \
+  int mgr_bwd_##SUFFIX(const void* x, const float* theta, const void* out, const void* gout, const void* sav, \
+                       void* gx, float* gtheta, void* ws, const mgr::Geometry& g, int flags, cudaStream_t s) { \
+    return mgr::backward_typed<T>(x, theta, out, gout, sav, gx, gtheta, ws, g, flags, s);                    \
   }

@@ -14,6 +14,7 @@
 namespace {
 thread_local char g_err[512] = "";
 std::atomic<long long> g_launches{0};
+std::atomic<int> g_debug_path{0};
 }
 
 namespace mgr {
@@ -29,6 +30,7 @@ int cuda_fail(cudaError_t e, const char* what) {
   return fail(MGR_ERR_CUDA_BASE + (int)e, "%s: %s", what, cudaGetErrorString(e));
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int debug_path() { return g_debug_path.load(std::memory_order_relaxed); }
 }  // namespace mgr
 
 namespace {
@@ -73,31 +75,47 @@ const char* mgr_build_info(void) {
 
 const char* mgr_last_error(void) { return g_err; }
 
+int mgr_set_debug_path(int path) {
+  if (path < 0 || path > 1) return fail(MGR_ERR_INVALID_ARGUMENT, "debug path %d unknown", path);
+  g_debug_path.store(path, std::memory_order_relaxed);
+  return MGR_OK;
+}
+
 long long mgr_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
-int mgr_render_forward(const void* x, const int64_t* x_strides, const float* theta, void* out, int B, int L, int H,
-                       int W, int dtype, int range_mode, void* stream) {
+size_t mgr_saved_alpha_bytes(int B, int L, int H, int W, int dtype) {
+  if (B <= 0 || L <= 0 || H <= 0 || W <= 0) return 0;
+  return (size_t)B * L * H * W * (dtype == MGR_F32 ? 4 : 2);
+}
+
+int mgr_render_forward(const void* x, const int64_t* x_strides, const float* theta, void* out, void* saved_alpha,
+                       int B, int L, int H, int W, int dtype, int range_mode, void* stream) {
   mgr::Geometry g;
   if (int rc = check_common(x, x_strides, B, L, H, W, dtype, range_mode, &g)) return rc;
   if (!out) return fail(MGR_ERR_INVALID_ARGUMENT, "out is NULL");
   if (B == 0) return MGR_OK;
   cudaStream_t s = (cudaStream_t)stream;
   switch (dtype) {
-    case MGR_F32: return mgr_fwd_f32(x, theta, out, g, s);
-    case MGR_BF16: return mgr_fwd_bf16(x, theta, out, g, s);
-    default: return mgr_fwd_f16(x, theta, out, g, s);
+    case MGR_F32: return mgr_fwd_f32(x, theta, out, saved_alpha, g, s);
+    case MGR_BF16: return mgr_fwd_bf16(x, theta, out, saved_alpha, g, s);
+    default: return mgr_fwd_f16(x, theta, out, saved_alpha, g, s);
   }
 }
 
 size_t mgr_render_backward_workspace_bytes(int B, int L, int H, int W, int dtype, int has_theta, int flags) {
-  if (B <= 0 || L <= 0 || H <= 0 || W <= 0) return 0;
-  if (has_theta && (flags & MGR_NEED_GRAD_X) && dtype != MGR_F32)
-    return sizeof(float) * (size_t)B * L * 4 * H * W;   // fp32 scatter accumulator
-  return 0;
+  if (B <= 0 || L <= 0 || H <= 0 || W <= 0 || !has_theta) return 0;
+  // tiled two-pass path: fp32 records (T_l a_l, d a_l) per layer-pixel + G_P per pixel
+  size_t need = ((size_t)B * L * H * W) * 8 + ((size_t)B * H * W) * 16;
+  // general direct-gather path with 16-bit storage: fp32 scatter accumulator
+  if ((flags & MGR_NEED_GRAD_X) && dtype != MGR_F32) {
+    const size_t scatter = sizeof(float) * (size_t)B * L * 4 * H * W;
+    if (scatter > need) need = scatter;
+  }
+  return need;
 }
 
 int mgr_render_backward(const void* x, const int64_t* x_strides, const float* theta, const void* out,
-                        const void* grad_out, void* grad_x, float* grad_theta, void* workspace,
+                        const void* grad_out, const void* saved_alpha, void* grad_x, float* grad_theta, void* workspace,
                         size_t workspace_bytes, int B, int L, int H, int W, int dtype, int range_mode, int flags,
                         void* stream) {
   mgr::Geometry g;
@@ -113,9 +131,9 @@ int mgr_render_backward(const void* x, const int64_t* x_strides, const float* th
     return fail(MGR_ERR_WORKSPACE_TOO_SMALL, "workspace %zu bytes < required %zu", workspace_bytes, need);
   cudaStream_t s = (cudaStream_t)stream;
   switch (dtype) {
-    case MGR_F32: return mgr_bwd_f32(x, theta, out, grad_out, grad_x, grad_theta, workspace, g, flags, s);
-    case MGR_BF16: return mgr_bwd_bf16(x, theta, out, grad_out, grad_x, grad_theta, workspace, g, flags, s);
-    default: return mgr_bwd_f16(x, theta, out, grad_out, grad_x, grad_theta, workspace, g, flags, s);
+    case MGR_F32: return mgr_bwd_f32(x, theta, out, grad_out, saved_alpha, grad_x, grad_theta, workspace, g, flags, s);
+    case MGR_BF16: return mgr_bwd_bf16(x, theta, out, grad_out, saved_alpha, grad_x, grad_theta, workspace, g, flags, s);
+    default: return mgr_bwd_f16(x, theta, out, grad_out, saved_alpha, grad_x, grad_theta, workspace, g, flags, s);
   }
 }
 

@@ -6,7 +6,8 @@
 namespace mgr {
 int fail(int code, const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
-void count_launch(int n = 1);   // process-wide count of kernels launched by this library
+void count_launch(int n = 1);
+int debug_path();                // 0 auto, 1 force the direct-gather kernels (tests / A-B timing)   // process-wide count of kernels launched by this library
 }  // namespace mgr
 
 #define MGR_CUDA(expr)                                        \

@@ -1,0 +1,309 @@
+// Tiled backward in two passes, no atomics on the pixel-gradient path.
+//
+// Pass 1  (render_bwd_pass1, one CTA per 32x32 OUTPUT tile, same staging as the forward):
+//   * pre-pass over the alpha samples saved by the forward: transmittance T_l in front of every
+//     layer (front -> back) and the composited alpha A = sum_l T_l a_l;
+//   * back -> front sweep with the layers re-sampled from staged footprints, carrying the canvas
+//     S_l, R_l behind the layer:   d c_l = G_P T_l a_l,   d a_l = T_l [G_P.(c_l - S_l) + G_A (1 - R_l)]
+//     (division-free in (1 - a_l), so exact at opaque texels);
+//   * writes one gradient record per (layer, pixel): (T_l a_l, d a_l), plus G_P per pixel -- the
+//     gradient w.r.t. the warped sample is (G_P * T_l a_l, d a_l);
+//   * grad_theta: d sample / d(ix, iy) comes for free from the lerp differences; reduced
+//     thread -> warp shuffle -> shared -> one atomicAdd per (CTA, layer, coefficient)  (A.1).
+//
+// Pass 2  (render_bwd_pass2, one thread per SOURCE texel): the bilinear adjoint in gather form.
+//   grad_x[t] = sum over output pixels p of  hat(ix(p) - x_t) * hat(iy(p) - y_t) * g(p),
+//   hat(u) = max(0, 1 - |u|).  The pixels that can touch texel t are the integer points of the
+//   parallelogram M^-1((x_t, y_t) + (-1,1)^2); they are enumerated over its bounding box, so every
+//   grad_x element is written exactly once, coalesced, in the storage dtype -- no zero-fill, no
+//   fp32 scatter buffer, no atomics, deterministic.
+//
+// Reference semantics: autograd of fukuwarai/networks.py:250-257 + custom/loss_aio.py:251
+// (ATen grid_sampler_2d_backward + affine_grid backward + the a_over_b chain).
+#pragma once
+#include "render_tiled.cuh"
+
+namespace mgr {
+
+// workspace layout of the tiled backward (all fp32):
+//   rec [B*L][H*W] float2 = (T_l a_l, d a_l)        gp [B][H*W] float4 = (G_P.rgb, unused)
+inline size_t bwd_tiled_ws_bytes(int B, int L, int H, int W) {
+  return ((size_t)B * L * H * W) * sizeof(float2) + ((size_t)B * H * W) * sizeof(float4);
+}
+
+template <typename T, bool kNeedTheta>
+__global__ void __launch_bounds__(kTiledThreads, 2)
+render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const T* __restrict__ out,
+                 const T* __restrict__ gout, const typename SavedAlpha<T>::type* __restrict__ sav,
+                 float2* __restrict__ rec, float4* __restrict__ gp, float* __restrict__ gtheta, Geometry g) {
+  using Vec = typename Texel<T>::Vec;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Vec* buf = reinterpret_cast<Vec*>(smem_raw);                                            // [kCapTexels]
+  LayerPlan* plan = reinterpret_cast<LayerPlan*>(smem_raw + sizeof(Vec) * kCapTexels);    // [L]
+  float* gth_acc = reinterpret_cast<float*>(plan + g.L);                                  // [L][6]
+  const int tid = threadIdx.x;
+  const int b = blockIdx.z;
+  const int j0 = blockIdx.x * kTW, i0 = blockIdx.y * kTH;
+  const int tx = tid & 31, ty = tid >> 5;
+  for (int l = tid; l < g.L; l += kTiledThreads)
+    plan[l] = plan_layer(theta + ((long long)b * g.L + l) * 6, g.H, g.W, j0, i0, kStageVec);
+  if (kNeedTheta)
+    for (int k = tid; k < g.L * 6; k += kTiledThreads) gth_acc[k] = 0.f;
+  __syncthreads();
+
+  const float zs = g.m11 ? 0.5f : 1.f;
+  const f32x2 zs2 = bc(zs), zb2 = bc(g.m11 ? 0.5f : 0.f);     // z = zs * raw + zb
+  const T* xb = x + (long long)b * g.sb;
+  const int hw = g.H * g.W;
+  const int j = j0 + tx;
+  const int pix0 = (i0 + ty) * g.W + j;                       // pixel k lives 8*k rows further down
+  const int row8 = 8 * g.W;
+  bool live[kPx];
+#pragma unroll
+  for (int k = 0; k < kPx; ++k) live[k] = j < g.W && i0 + ty + 8 * k < g.H;
+  float2* recb = rec + (long long)b * g.L * hw + pix0;
+  const typename SavedAlpha<T>::type* savb = sav + (long long)b * g.L * hw + pix0;
+
+  // ---- pre-pass: T_l (parked in rec[l].x until the sweep replaces it) and A ----------------------
+  float GP0[kPx], GP1[kPx], GP2[kPx], GA[kPx];
+  {
+    float Tc[kPx], A[kPx];
+#pragma unroll
+    for (int k = 0; k < kPx; ++k) { Tc[k] = 1.f; A[k] = 0.f; }
+    for (int l = g.L - 1; l >= 0; --l) {
+#pragma unroll
+      for (int k = 0; k < kPx; ++k) {
+        if (live[k]) {
+          const float a = ld_alpha(savb + (long long)l * hw + k * row8);
+          recb[(long long)l * hw + k * row8].x = Tc[k];
+          A[k] = fmaf(Tc[k], a, A[k]);
+          Tc[k] *= (1.f - a);
+        }
+      }
+    }
+    // upstream gradient in the compositing domain: o = P / A
+    const float gs = g.m11 ? 2.f : 1.f;                       // d out / d o
+    const float is = g.m11 ? 0.5f : 1.f, ib = g.m11 ? 0.5f : 0.f;
+    const T* gob = gout + (long long)b * 4 * hw + pix0;
+    const T* ob_ = out + (long long)b * 4 * hw + pix0;
+#pragma unroll
+    for (int k = 0; k < kPx; ++k) {
+      GP0[k] = GP1[k] = GP2[k] = GA[k] = 0.f;
+      if (live[k]) {
+        const float g0 = gs * ld(gob + k * row8), g1 = gs * ld(gob + k * row8 + hw),
+                    g2 = gs * ld(gob + k * row8 + 2 * hw), g3 = gs * ld(gob + k * row8 + 3 * hw);
+        if (A[k] != 0.f) {                                    // A == 0: every gradient is defined as 0
+          const float inv = 1.f / A[k];
+          const float o0 = fmaf(ld(ob_ + k * row8), is, ib), o1 = fmaf(ld(ob_ + k * row8 + hw), is, ib),
+                      o2 = fmaf(ld(ob_ + k * row8 + 2 * hw), is, ib);
+          GP0[k] = g0 * inv; GP1[k] = g1 * inv; GP2[k] = g2 * inv;
+          GA[k] = g3 - (g0 * o0 + g1 * o1 + g2 * o2) * inv;
+        }
+        gp[(long long)b * hw + pix0 + k * row8] = make_float4(GP0[k], GP1[k], GP2[k], 0.f);
+      }
+    }
+  }
+
+  // ---- back -> front sweep ------------------------------------------------------------------------
+  const float djf = (float)(tx - kTW / 2);
+  const float xj = norm_coord(j, g.W);
+  const float hW = 0.5f * (float)g.W * zs, hH = 0.5f * (float)g.H * zs;   // d ix / d gx (and the range scale)
+  float S0[kPx], S1[kPx], S2[kPx], R[kPx];
+#pragma unroll
+  for (int k = 0; k < kPx; ++k) S0[k] = S1[k] = S2[k] = R[k] = 0.f;
+
+  for (int l = 0; l < g.L; ++l) {
+    const LayerPlan& p = plan[l];
+    const int mode = p.mode;
+    float2* rl = recb + (long long)l * hw;
+    if (mode == kSkip) {                     // a = 0, c undefined: no colour gradient; d a_l is still defined
+#pragma unroll
+      for (int k = 0; k < kPx; ++k) {
+        if (live[k]) {
+          const float T_l = rl[k * row8].x;
+          // c_l = 0 in the compositing domain (transparent black)
+          const float ga = T_l * (-(GP0[k] * S0[k] + GP1[k] * S1[k] + GP2[k] * S2[k]) + GA[k] * (1.f - R[k]));
+          rl[k * row8] = make_float2(0.f, ga);
+        }
+      }
+      continue;                              // the footprint misses the image: no texel, no theta gradient
+    }
+    const T* img = xb + (long long)l * g.sl;
+    if (mode == kStaged) {
+      __syncthreads();
+      stage_footprint<T>(img, g, p, buf, tid);
+      __syncthreads();
+    }
+    const float a01 = p.aff.a01, a11 = p.aff.a11;
+    const float bx = fmaf(p.aff.a00, djf, p.lrx), by = fmaf(p.aff.a10, djf, p.lry);
+    const int pitch = p.bw;
+    float accx = 0.f, accxy = 0.f, accy = 0.f, accyy = 0.f;
+#pragma unroll
+    for (int k = 0; k < kPx; ++k) {
+      float r_, g_, b_, a;
+      float dxr, dxg, dxb, dxa, dyr, dyg, dyb, dya;
+      if (mode == kStaged) {
+        const float dif = (float)(ty + 8 * k - kTH / 2);
+        const float ix = fmaf(a01, dif, bx), iy = fmaf(a11, dif, by);
+        const float fxf = floorf(ix), fyf = floorf(iy);
+        const SampleGrad s = sample_staged_grad<T>(buf + (int)fyf * pitch + (int)fxf, pitch, ix - fxf, iy - fyf);
+        upk(fma2(s.rg, zs2, zb2), r_, g_);
+        upk(fma2(s.ba, zs2, zb2), b_, a);
+        upk(s.dx_rg, dxr, dxg); upk(s.dx_ba, dxb, dxa);
+        upk(s.dy_rg, dyr, dyg); upk(s.dy_ba, dyb, dya);
+      } else {
+        // huge footprint: bounds-checked taps straight from global memory
+        const Taps tp = make_taps(p.aff, tx - kTW / 2, ty + 8 * k - kTH / 2, g.H, g.W, g.sh);
+        const float shift = g.m11 ? 1.f : 0.f;
+        float v[4][4], zz[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const T* pl = img + c * g.sc;
+          v[c][0] = (tp.mask & 1u) ? ld(pl + tp.o00) + shift : 0.f;
+          v[c][1] = (tp.mask & 2u) ? ld(pl + tp.o01) + shift : 0.f;
+          v[c][2] = (tp.mask & 4u) ? ld(pl + tp.o10) + shift : 0.f;
+          v[c][3] = (tp.mask & 8u) ? ld(pl + tp.o11) + shift : 0.f;
+          zz[c] = zs * fmaf(v[c][3], tp.w11, fmaf(v[c][2], tp.w10, fmaf(v[c][1], tp.w01, v[c][0] * tp.w00)));
+        }
+        const float ex = 1.f - tp.fx, ey = 1.f - tp.fy;
+        r_ = zz[0]; g_ = zz[1]; b_ = zz[2]; a = zz[3];
+        dxr = (v[0][1] - v[0][0]) * ey + (v[0][3] - v[0][2]) * tp.fy; dyr = (v[0][2] - v[0][0]) * ex + (v[0][3] - v[0][1]) * tp.fx;
+        dxg = (v[1][1] - v[1][0]) * ey + (v[1][3] - v[1][2]) * tp.fy; dyg = (v[1][2] - v[1][0]) * ex + (v[1][3] - v[1][1]) * tp.fx;
+        dxb = (v[2][1] - v[2][0]) * ey + (v[2][3] - v[2][2]) * tp.fy; dyb = (v[2][2] - v[2][0]) * ex + (v[2][3] - v[2][1]) * tp.fx;
+        dxa = (v[3][1] - v[3][0]) * ey + (v[3][3] - v[3][2]) * tp.fy; dya = (v[3][2] - v[3][0]) * ex + (v[3][3] - v[3][1]) * tp.fx;
+      }
+      float T_l = 0.f;
+      if (live[k]) T_l = rl[k * row8].x;
+      const float ta = T_l * a;
+      const float ga = T_l * (GP0[k] * (r_ - S0[k]) + GP1[k] * (g_ - S1[k]) + GP2[k] * (b_ - S2[k]) + GA[k] * (1.f - R[k]));
+      if (live[k]) rl[k * row8] = make_float2(ta, ga);
+      if (kNeedTheta) {
+        const float gr = GP0[k] * ta, gg = GP1[k] * ta, gb = GP2[k] * ta;
+        const float dix = fmaf(gr, dxr, fmaf(gg, dxg, fmaf(gb, dxb, ga * dxa)));
+        const float diy = fmaf(gr, dyr, fmaf(gg, dyg, fmaf(gb, dyb, ga * dya)));
+        const float yi = norm_coord(i0 + ty + 8 * k, g.H);
+        accx += dix; accxy = fmaf(dix, yi, accxy);
+        accy += diy; accyy = fmaf(diy, yi, accyy);
+      }
+      const float om = 1.f - a;
+      S0[k] = fmaf(om, S0[k], a * r_);
+      S1[k] = fmaf(om, S1[k], a * g_);
+      S2[k] = fmaf(om, S2[k], a * b_);
+      R[k] = fmaf(om, R[k], a);
+    }
+    if (kNeedTheta) {
+      // this thread's four pixels share the column: (ggx x_j, ggx y_i, ggx, ggy x_j, ggy y_i, ggy)
+      float part[6] = {hW * accx * xj, hW * accxy, hW * accx, hH * accy * xj, hH * accyy, hH * accy};
+#pragma unroll
+      for (int q = 0; q < 6; ++q) {
+        const float s = warp_sum(part[q]);
+        if (tx == 0) atomicAdd(&gth_acc[l * 6 + q], s);
+      }
+    }
+  }
+  if (kNeedTheta) {
+    __syncthreads();
+    for (int k = tid; k < g.L * 6; k += kTiledThreads) atomicAdd(gtheta + (long long)b * g.L * 6 + k, gth_acc[k]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2: gather-form bilinear adjoint, one thread per source texel, block = 32 x 8 texels
+// ---------------------------------------------------------------------------------------------
+struct InversePlan {
+  float a00, a01, a10, a11;     // forward map, pixel space: (ix, iy) = A (j, i) + c
+  float i00, i01, i10, i11;     // A^-1
+  float jcf, icf;               // fractional part of the pre-image of the block centre
+  int JC, IC;                   // integer part
+  float rj, ri;                 // half extents of the pre-image of a texel's (-1,1)^2 support
+  int valid;                    // 0: non-finite or singular placement -> grad_x of this layer is 0
+};
+
+constexpr int kP2W = 32, kP2H = 8;
+
+template <typename T>
+__global__ void __launch_bounds__(kP2W * kP2H)
+render_bwd_pass2(const float* __restrict__ theta, const float2* __restrict__ rec, const float4* __restrict__ gp,
+                 T* __restrict__ gx, Geometry g) {
+  __shared__ InversePlan ip;
+  const int n = blockIdx.z;                     // b * L + l
+  const int b = n / g.L;
+  const int x0b = blockIdx.x * kP2W, y0b = blockIdx.y * kP2H;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    const float* th = theta + (long long)n * 6;
+    const double w = g.W, h = g.H;
+    const double a00 = th[0], a01 = th[1] * (w / h), a10 = th[3] * (h / w), a11 = th[4];
+    const double c0 = a00 * (0.5 - 0.5 * w) + a01 * (0.5 - 0.5 * h) + th[2] * 0.5 * w + 0.5 * (w - 1.0);
+    const double c1 = a10 * (0.5 - 0.5 * w) + a11 * (0.5 - 0.5 * h) + th[5] * 0.5 * h + 0.5 * (h - 1.0);
+    const double det = a00 * a11 - a01 * a10;
+    InversePlan q;
+    q.a00 = (float)a00; q.a01 = (float)a01; q.a10 = (float)a10; q.a11 = (float)a11;
+    q.valid = 0;
+    const double xc = x0b + 0.5 * kP2W, yc = y0b + 0.5 * kP2H;      // block centre (source space)
+    const double inv = 1.0 / det;
+    const double i00 = a11 * inv, i01 = -a01 * inv, i10 = -a10 * inv, i11 = a00 * inv;
+    const double jc = i00 * (xc - c0) + i01 * (yc - c1), ic = i10 * (xc - c0) + i11 * (yc - c1);
+    const double rj = fabs(i00) + fabs(i01), ri = fabs(i10) + fabs(i11);
+    q.i00 = (float)i00; q.i01 = (float)i01; q.i10 = (float)i10; q.i11 = (float)i11;
+    q.JC = q.IC = 0; q.jcf = q.icf = 0.f; q.rj = q.ri = 0.f;
+    if (isfinite(jc) && isfinite(ic) && isfinite(rj) && isfinite(ri)) {
+      // a block whose pre-image is far outside the output image cannot be touched by any pixel
+      const double far = 4.0 * (w + h) + 64.0 * (rj + ri);
+      if (fabs(jc) < far + 1.0e6 && fabs(ic) < far + 1.0e6 && rj < 1.0e6 && ri < 1.0e6) {
+        const double fj = floor(jc), fi = floor(ic);
+        q.JC = (int)fj; q.IC = (int)fi; q.jcf = (float)(jc - fj); q.icf = (float)(ic - fi);
+        q.rj = (float)rj * 1.0001f + 1e-3f; q.ri = (float)ri * 1.0001f + 1e-3f;
+        q.valid = 1;
+      }
+    }
+    ip = q;
+  }
+  __syncthreads();
+  const int x = x0b + tx, y = y0b + ty;
+  if (x >= g.W || y >= g.H) return;
+  const int hw = g.H * g.W;
+  T* gxp = gx + (long long)n * 4 * hw + y * g.W + x;
+  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+  if (ip.valid) {
+    const float dxl = (float)tx - 0.5f * kP2W, dyl = (float)ty - 0.5f * kP2H;   // texel - block centre
+    // pre-image of this texel relative to (JC, IC); candidates are the integer points within (rj, ri) of it,
+    // clamped to the output image (all in float first: the window of a near-singular placement is huge)
+    const float pj = ip.jcf + ip.i00 * dxl + ip.i01 * dyl;
+    const float pi = ip.icf + ip.i10 * dxl + ip.i11 * dyl;
+    const float mlo = fmaxf(ceilf(pj - ip.rj), (float)(-ip.JC)), mhi = fminf(floorf(pj + ip.rj), (float)(g.W - 1 - ip.JC));
+    const float nlo = fmaxf(ceilf(pi - ip.ri), (float)(-ip.IC)), nhi = fminf(floorf(pi + ip.ri), (float)(g.H - 1 - ip.IC));
+    if (mlo <= mhi && nlo <= nhi) {
+      const int m0 = (int)mlo, m1 = (int)mhi, n0 = (int)nlo, n1 = (int)nhi;
+      const float2* recn = rec + (long long)n * hw;
+      const float4* gpb = gp + (long long)b * hw;
+      for (int nn = n0; nn <= n1; ++nn) {
+        const float di = (float)nn - ip.icf;
+        const float ub = fmaf(ip.a01, di, -dxl), vb = fmaf(ip.a11, di, -dyl);
+        const int rowoff = (ip.IC + nn) * g.W + ip.JC;
+        for (int mm = m0; mm <= m1; ++mm) {
+          const float dj = (float)mm - ip.jcf;
+          const float u = fmaf(ip.a00, dj, ub), v = fmaf(ip.a10, dj, vb);    // (ix, iy)(candidate) - (x, y)
+          const float wx = 1.f - fabsf(u), wy = 1.f - fabsf(v);
+          if (wx > 0.f && wy > 0.f) {
+            const float wgt = wx * wy;
+            const float2 r = __ldg(recn + rowoff + mm);
+            const float4 G = __ldg(gpb + rowoff + mm);
+            const float wt = wgt * r.x;
+            acc0 = fmaf(wt, G.x, acc0);
+            acc1 = fmaf(wt, G.y, acc1);
+            acc2 = fmaf(wt, G.z, acc2);
+            acc3 = fmaf(wgt, r.y, acc3);
+          }
+        }
+      }
+    }
+  }
+  const float zs = g.m11 ? 0.5f : 1.f;          // d z / d x_texel = zs * weight
+  st(gxp, zs * acc0);
+  st(gxp + hw, zs * acc1);
+  st(gxp + 2 * hw, zs * acc2);
+  st(gxp + 3 * hw, zs * acc3);
+}
+
+}  // namespace mgr

@@ -70,14 +70,18 @@ class _Render(torch.autograd.Function):
         xk, strides = _x_arg(x.detach())
         th = None if theta is None else theta.detach().to(torch.float32).contiguous()
         out = torch.empty((B, 4, H, W), dtype=x.dtype, device=x.device)
+        # alpha samples for the atomics-free backward: only when a gradient will be asked for
+        sav = None
+        if th is not None and any(ctx.needs_input_grad[:2]):
+            sav = torch.empty(lib.mgr_saved_alpha_bytes(B, L, H, W, _DTYPES[x.dtype]), dtype=torch.uint8, device=x.device)
         with torch.cuda.device(x.device):
-            rc = lib.mgr_render_forward(_ptr(xk), strides, _ptr(th), _ptr(out), B, L, H, W, _DTYPES[x.dtype],
+            rc = lib.mgr_render_forward(_ptr(xk), strides, _ptr(th), _ptr(out), _ptr(sav), B, L, H, W, _DTYPES[x.dtype],
                                         _RANGES[in_range], _stream_ptr(x.device))
         _lib.check(rc, "mgr_render_forward")
         _lib.launch_count += 1
         ctx.in_range = in_range
         ctx.theta_dtype = None if theta is None else theta.dtype
-        ctx.save_for_backward(xk, th, out)
+        ctx.save_for_backward(xk, th, out, sav)
         ctx.x_strides = strides
         return out
 
@@ -85,7 +89,7 @@ class _Render(torch.autograd.Function):
     @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
         lib = _lib.load()
-        xk, th, out = ctx.saved_tensors
+        xk, th, out, sav = ctx.saved_tensors
         B, L, _, H, W = xk.shape
         need_x = ctx.needs_input_grad[0]
         need_t = th is not None and ctx.needs_input_grad[1]
@@ -99,7 +103,7 @@ class _Render(torch.autograd.Function):
         ws_bytes = lib.mgr_render_backward_workspace_bytes(B, L, H, W, dt, int(th is not None), flags)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xk.device) if ws_bytes else None
         with torch.cuda.device(xk.device):
-            rc = lib.mgr_render_backward(_ptr(xk), ctx.x_strides, _ptr(th), _ptr(out), _ptr(go), _ptr(gx), _ptr(gt),
+            rc = lib.mgr_render_backward(_ptr(xk), ctx.x_strides, _ptr(th), _ptr(out), _ptr(go), _ptr(sav), _ptr(gx), _ptr(gt),
                                          _ptr(ws), ws_bytes, B, L, H, W, dt, _RANGES[ctx.in_range], flags,
                                          _stream_ptr(xk.device))
         _lib.check(rc, "mgr_render_backward")

@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define MGR_ABI_VERSION 1
+#define MGR_ABI_VERSION 2
 
 enum { MGR_F32 = 0, MGR_BF16 = 1, MGR_F16 = 2 };
 enum { MGR_RANGE_M11 = 0, MGR_RANGE_01 = 1 };
@@ -69,15 +69,29 @@ const char* mgr_last_error(void);
 /* Number of CUDA kernels this library has launched in this process (all threads, all calls);
  * bench.py differences it around the timed region to report "gpu_launches". */
 long long mgr_kernel_launch_count(void);
+/* Testing / A-B timing only: 0 = automatic kernel selection (default), 1 = force the general
+ * direct-gather kernels even where the tiled shared-memory kernels apply.  Process-wide. */
+int mgr_set_debug_path(int path);
+
+/*
+ * Bytes of the optional "saved alpha" buffer [B,L,H,W] the forward can fill for the backward:
+ * the warped alpha sample of every (layer, pixel), fp32 for MGR_F32 tensors, fp16 otherwise.
+ * (What autograd would keep alive in the reference is 13x larger: the grid, the warped layers and
+ * every a_over_b intermediate.)
+ */
+size_t mgr_saved_alpha_bytes(int B, int L, int H, int W, int dtype);
 
 /*
  * Fused warp + composite, forward.
  *   replaces: fukuwarai/networks.py:250-257 + custom/loss_aio.py:251 (theta != NULL)
  *             custom/loss_aio.py:251 alone on the real branch :313-320 (theta == NULL)
- * out is written completely.
+ *   out          written completely
+ *   saved_alpha  NULL (inference), or mgr_saved_alpha_bytes(...) bytes written completely when
+ *                theta != NULL; pass it to mgr_render_backward to enable the atomics-free backward
  */
 int mgr_render_forward(const void* x, const int64_t* x_strides, const float* theta, void* out,
-                       int B, int L, int H, int W, int dtype, int range_mode, void* stream);
+                       void* saved_alpha, int B, int L, int H, int W, int dtype, int range_mode,
+                       void* stream);
 
 /*
  * Bytes of scratch mgr_render_backward needs for this problem (0 is possible).
@@ -87,19 +101,21 @@ size_t mgr_render_backward_workspace_bytes(int B, int L, int H, int W, int dtype
 
 /*
  * Fused warp + composite, backward (the autograd of the chain above).
- *   out       saved forward result [B,4,H,W] (same dtype), read-only
- *   grad_out  [B,4,H,W] contiguous
- *   grad_x    [B,L,4,H,W] contiguous, written completely (no pre-zeroing needed); may be NULL
- *             when flags lacks MGR_NEED_GRAD_X
- *   grad_theta[B,L,2,3] float32, written completely; may be NULL when theta is NULL or flags
- *             lacks MGR_NEED_GRAD_THETA
- *   workspace device scratch of at least mgr_render_backward_workspace_bytes(...) bytes,
- *             256-byte aligned; contents undefined on entry and exit
+ *   out         saved forward result [B,4,H,W] (same dtype), read-only
+ *   grad_out    [B,4,H,W] contiguous
+ *   saved_alpha what the forward wrote, or NULL (then the general scatter kernels run)
+ *   grad_x      [B,L,4,H,W] contiguous, written completely (no pre-zeroing needed); may be NULL
+ *               when flags lacks MGR_NEED_GRAD_X
+ *   grad_theta  [B,L,2,3] float32, written completely; may be NULL when theta is NULL or flags
+ *               lacks MGR_NEED_GRAD_THETA
+ *   workspace   device scratch of at least mgr_render_backward_workspace_bytes(...) bytes,
+ *               256-byte aligned; contents undefined on entry and exit
  */
 int mgr_render_backward(const void* x, const int64_t* x_strides, const float* theta,
-                        const void* out, const void* grad_out, void* grad_x, float* grad_theta,
-                        void* workspace, size_t workspace_bytes, int B, int L, int H, int W,
-                        int dtype, int range_mode, int flags, void* stream);
+                        const void* out, const void* grad_out, const void* saved_alpha,
+                        void* grad_x, float* grad_theta, void* workspace, size_t workspace_bytes,
+                        int B, int L, int H, int W, int dtype, int range_mode, int flags,
+                        void* stream);
 
 #ifdef __cplusplus
 }

@@ -61,7 +61,7 @@ def test_forward_argument_validation(args, code):
     lib = _lib.load()
     a = dict(x=0x1000, theta=None, out=0x2000, B=1, L=2, H=4, W=4, dtype=0, range_mode=0)
     a.update(args)
-    rc = lib.mgr_render_forward(a["x"], None, a["theta"], a["out"], a["B"], a["L"], a["H"], a["W"], a["dtype"],
+    rc = lib.mgr_render_forward(a["x"], None, a["theta"], a["out"], None, a["B"], a["L"], a["H"], a["W"], a["dtype"],
                                 a["range_mode"], None)
     assert rc == code
     assert lib.mgr_last_error()
@@ -70,22 +70,25 @@ def test_forward_argument_validation(args, code):
 def test_strided_w_rejected():
     lib = _lib.load()
     strides = (ctypes.c_int64 * 5)(512, 128, 32, 8, 2)
-    rc = lib.mgr_render_forward(0x1000, strides, None, 0x2000, 1, 2, 4, 4, 0, 0, None)
+    rc = lib.mgr_render_forward(0x1000, strides, None, 0x2000, None, 1, 2, 4, 4, 0, 0, None)
     assert rc == 2 and b"stride" in lib.mgr_last_error()
 
 
 def test_backward_validation_and_workspace():
     lib = _lib.load()
-    assert lib.mgr_render_backward_workspace_bytes(2, 3, 8, 8, _lib.MGR_F32, 1, 3) == 0
+    assert lib.mgr_render_backward_workspace_bytes(2, 3, 8, 8, _lib.MGR_F32, 0, 3) == 0      # composite only
     assert lib.mgr_render_backward_workspace_bytes(2, 3, 8, 8, _lib.MGR_BF16, 0, 1) == 0
+    assert lib.mgr_render_backward_workspace_bytes(2, 3, 8, 8, _lib.MGR_F32, 1, 3) == 2 * 3 * 64 * 8 + 2 * 64 * 16
+    assert lib.mgr_saved_alpha_bytes(2, 3, 8, 8, _lib.MGR_F32) == 2 * 3 * 64 * 4
+    assert lib.mgr_saved_alpha_bytes(2, 3, 8, 8, _lib.MGR_BF16) == 2 * 3 * 64 * 2
     need = lib.mgr_render_backward_workspace_bytes(2, 3, 8, 8, _lib.MGR_BF16, 1, 3)
-    rc = lib.mgr_render_backward(0x1000, None, 0x3000, 0x2000, 0x2000, 0x4000, 0x5000, None, 0, 2, 3, 8, 8,
+    assert need == 2 * 3 * 4 * 64 * 4                # fp32 scatter accumulator of the general path dominates
+    rc = lib.mgr_render_backward(0x1000, None, 0x3000, 0x2000, 0x2000, None, 0x4000, 0x5000, None, 0, 2, 3, 8, 8,
                                  _lib.MGR_BF16, 0, 3, None)
-    if need:
-        assert rc == 3 and b"workspace" in lib.mgr_last_error()
-    rc = lib.mgr_render_backward(0x1000, None, None, 0x2000, 0x2000, None, None, None, 0, 2, 3, 8, 8, 0, 0, 1, None)
+    assert rc == 3 and b"workspace" in lib.mgr_last_error()
+    rc = lib.mgr_render_backward(0x1000, None, None, 0x2000, 0x2000, None, None, None, None, 0, 2, 3, 8, 8, 0, 0, 1, None)
     assert rc == 1                                   # grad_x requested but NULL
-    rc = lib.mgr_render_backward(0x1000, None, None, 0x2000, 0x2000, None, None, None, 0, 2, 3, 8, 8, 0, 0, 0, None)
+    rc = lib.mgr_render_backward(0x1000, None, None, 0x2000, 0x2000, None, None, None, None, 0, 2, 3, 8, 8, 0, 0, 0, None)
     assert rc == 0                                   # nothing requested: no-op
-    rc = lib.mgr_render_forward(0x1000, None, None, 0x2000, 0, 3, 8, 8, 0, 0, None)
+    rc = lib.mgr_render_forward(0x1000, None, None, 0x2000, None, 0, 3, 8, 8, 0, 0, None)
     assert rc == 0                                   # empty batch: no-op

@@ -106,10 +106,9 @@ def test_ragged_shapes(shape):
     th = synth.make_theta(B, L, "I", seed=5)
     go = synth.make_grad_out(B, H, W, "randn", seed=5)
     new = _run_cuda(x, th, go)
+    r32 = R.render_fwd_bwd(x.numpy(), th.numpy(), go.numpy(), "m11", np.float32)
     r64 = R.render_fwd_bwd(x.numpy(), th.numpy(), go.numpy(), "m11", np.float64)
-    assert max_abs(new["out"], r64["out"]) < FWD_TOL
-    assert rel_err(new["grad_x"], r64["grad_x"]) < GRAD_TOL
-    assert rel_err(new["grad_theta"], r64["grad_theta"]) < 5e-4
+    _assert_three_way(new, r32, r64, shape)
 
 
 @pytest.mark.parametrize("in_range", ["m11", "01"])
@@ -133,9 +132,12 @@ def test_strided_input_views():
     x = big[1:B + 1, :, :, :, 3:W + 3]
     assert not x.is_contiguous()
     th = synth.make_theta(B, L, "I", seed=2).to(DEV)
-    a = mr.render(x, th)
-    b = mr.render(x.contiguous(), th)
-    assert torch.equal(a, b)
+    a = mr.render(x, th)                    # unaligned view: general direct-gather kernels
+    b = mr.render(x.contiguous(), th)       # aligned: tiled kernels
+    assert (a - b).abs().max().item() < 5e-5
+    big4 = synth.make_layers(B + 2, L, H, W + 8, "W", seed=2).to(DEV)
+    x4 = big4[1:B + 1, :, :, :, 4:W + 4]     # still vector-aligned: strides go to the tiled kernels untouched
+    assert torch.equal(mr.render(x4, th), mr.render(x4.contiguous(), th))
     xs = x.detach().requires_grad_(True)
     xc = x.detach().contiguous().requires_grad_(True)
     go = synth.make_grad_out(B, H, W, seed=2).to(DEV)
@@ -225,3 +227,33 @@ def test_full_size_properties_config2():
     out.backward(g1)
     assert xo.grad[:, :L - 1].abs().max().item() == 0.0
     assert (out[:, 3] == 1).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
+@pytest.mark.parametrize("tf", ["I", "T", "X", "0"])
+def test_tiled_kernels_match_direct_kernels(dtype, tf):
+    """The shared-memory tiled kernels and the general direct-gather kernels are two
+    implementations of the same math: outputs agree to rounding (fp32) / one storage ulp."""
+    from montage_gan_b200 import _lib
+    lib = _lib.load()
+    B, L, H, W = 3, 6, 96, 80
+    x = synth.make_layers(B, L, H, W, "F", seed=3).to(DEV, dtype)
+    th = synth.make_theta(B, L, tf, seed=3, cover_back=False).to(DEV)
+    go = synth.make_grad_out(B, H, W, seed=3).to(DEV, dtype)
+    res = []
+    for path in (0, 1):
+        lib.mgr_set_debug_path(path)
+        try:
+            xx, tt = x.clone().requires_grad_(True), th.clone().requires_grad_(True)
+            out = mr.render(xx, tt)
+            out.backward(go)
+            res.append((out.detach().float().cpu().numpy(), xx.grad.float().cpu().numpy(), tt.grad.cpu().numpy()))
+        finally:
+            lib.mgr_set_debug_path(0)
+    # 'F' layers have hard 0/1 alpha edges over noise colours: o = P/A amplifies the ~1e-6 px difference in
+    # coordinate rounding between the two kernels where A is small; parity proper is judged against the oracle
+    tol = 5e-5 if dtype == torch.float32 else 2 ** -7
+    assert max_abs(res[0][0], res[1][0]) <= tol
+    assert rel_err(res[0][1], res[1][1]) <= (1e-5 if dtype == torch.float32 else 2 ** -6)
+    if tf != "0":       # identity placement: floor() flips make grad_theta ill-conditioned (SURVEY finding 4)
+        assert rel_err(res[0][2], res[1][2]) <= (1e-4 if dtype == torch.float32 else 5e-2)
