@@ -85,14 +85,16 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
     const bool nx = flags & MGR_NEED_GRAD_X, nt = flags & MGR_NEED_GRAD_THETA;
     float2* rec = reinterpret_cast<float2*>(ws);
     float4* gp = reinterpret_cast<float4*>(reinterpret_cast<char*>(ws) + sizeof(float2) * (size_t)g.B * g.L * g.H * g.W);
+    InverseLayer* inv = reinterpret_cast<InverseLayer*>(reinterpret_cast<char*>(gp) + sizeof(float4) * (size_t)g.B * g.H * g.W);
     static bool configured = false;
     if (!configured) {
-      MGR_CUDA(cudaFuncSetAttribute(render_bwd_pass1<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      MGR_CUDA(cudaFuncSetAttribute(render_bwd_pass1<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      MGR_CUDA(cudaFuncSetAttribute(render_bwd_pass1<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      MGR_CUDA(cudaFuncSetAttribute(render_bwd_pass1<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       configured = true;
     }
     if (nt) MGR_CUDA(cudaMemsetAsync(gtheta, 0, sizeof(float) * 6 * g.B * g.L, s));
-    const size_t smem = tiled_smem_bytes(g.L, sizeof(Vec)) + sizeof(float) * 6 * g.L;
+    const size_t smem = tiled_smem_bytes(g.L, sizeof(Vec)) + sizeof(float) * 6 * g.L +
+                        sizeof(float) * (size_t)g.L * kPx * kTiledThreads;          // + transmittance stash
     dim3 grid((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B);
     if (nt)
       render_bwd_pass1<T, true><<<grid, kTiledThreads, smem, s>>>((const T*)x, theta, (const T*)out, (const T*)gout,
@@ -104,7 +106,10 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
     count_launch();
     if (nx) {
       dim3 grid2((g.W + kP2W - 1) / kP2W, (g.H + kP2H - 1) / kP2H, g.B * g.L);
-      render_bwd_pass2<T><<<grid2, kP2W * kP2H, 0, s>>>(theta, rec, gp, (T*)gx, g);
+      inverse_plans_kernel<<<(g.B * g.L + 127) / 128, 128, 0, s>>>(theta, inv, g.B * g.L, g.H, g.W);
+      MGR_CUDA(cudaGetLastError());
+      count_launch();
+      render_bwd_pass2<T><<<grid2, kP2W * kP2H, 0, s>>>(inv, rec, gp, (T*)gx, g);
       MGR_CUDA(cudaGetLastError());
       count_launch();
     }

@@ -27,9 +27,7 @@ namespace mgr {
 
 // workspace layout of the tiled backward (all fp32):
 //   rec [B*L][H*W] float2 = (T_l a_l, d a_l)        gp [B][H*W] float4 = (G_P.rgb, unused)
-inline size_t bwd_tiled_ws_bytes(int B, int L, int H, int W) {
-  return ((size_t)B * L * H * W) * sizeof(float2) + ((size_t)B * H * W) * sizeof(float4);
-}
+//   inverse plans [B*L] InverseLayer (128 B each)
 
 template <typename T, bool kNeedTheta>
 __global__ void __launch_bounds__(kTiledThreads, 2)
@@ -42,6 +40,7 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
   LayerPlan* plan = reinterpret_cast<LayerPlan*>(smem_raw + sizeof(Vec) * kCapTexels);    // [L]
   float* gth_acc = reinterpret_cast<float*>(plan + g.L);                                  // [L][6]
   const int tid = threadIdx.x;
+  float* Tst = gth_acc + 6 * g.L + tid;                     // [L][kPx][256]: transmittance in front of layer l
   const int b = blockIdx.z;
   const int j0 = blockIdx.x * kTW, i0 = blockIdx.y * kTH;
   const int tx = tid & 31, ty = tid >> 5;
@@ -64,7 +63,7 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
   float2* recb = rec + (long long)b * g.L * hw + pix0;
   const typename SavedAlpha<T>::type* savb = sav + (long long)b * g.L * hw + pix0;
 
-  // ---- pre-pass: T_l (parked in rec[l].x until the sweep replaces it) and A ----------------------
+  // ---- pre-pass: T_l (stashed in shared memory) and A ------------------------------------------------
   float GP0[kPx], GP1[kPx], GP2[kPx], GA[kPx];
   {
     float Tc[kPx], A[kPx];
@@ -73,9 +72,9 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
     for (int l = g.L - 1; l >= 0; --l) {
 #pragma unroll
       for (int k = 0; k < kPx; ++k) {
+        Tst[(l * kPx + k) * kTiledThreads] = live[k] ? Tc[k] : 0.f;
         if (live[k]) {
           const float a = ld_alpha(savb + (long long)l * hw + k * row8);
-          recb[(long long)l * hw + k * row8].x = Tc[k];
           A[k] = fmaf(Tc[k], a, A[k]);
           Tc[k] *= (1.f - a);
         }
@@ -120,7 +119,7 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
 #pragma unroll
       for (int k = 0; k < kPx; ++k) {
         if (live[k]) {
-          const float T_l = rl[k * row8].x;
+          const float T_l = Tst[(l * kPx + k) * kTiledThreads];
           // c_l = 0 in the compositing domain (transparent black)
           const float ga = T_l * (-(GP0[k] * S0[k] + GP1[k] * S1[k] + GP2[k] * S2[k]) + GA[k] * (1.f - R[k]));
           rl[k * row8] = make_float2(0.f, ga);
@@ -172,8 +171,7 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
         dxb = (v[2][1] - v[2][0]) * ey + (v[2][3] - v[2][2]) * tp.fy; dyb = (v[2][2] - v[2][0]) * ex + (v[2][3] - v[2][1]) * tp.fx;
         dxa = (v[3][1] - v[3][0]) * ey + (v[3][3] - v[3][2]) * tp.fy; dya = (v[3][2] - v[3][0]) * ex + (v[3][3] - v[3][1]) * tp.fx;
       }
-      float T_l = 0.f;
-      if (live[k]) T_l = rl[k * row8].x;
+      const float T_l = Tst[(l * kPx + k) * kTiledThreads];
       const float ta = T_l * a;
       const float ga = T_l * (GP0[k] * (r_ - S0[k]) + GP1[k] * (g_ - S1[k]) + GP2[k] * (b_ - S2[k]) + GA[k] * (1.f - R[k]));
       if (live[k]) rl[k * row8] = make_float2(ta, ga);
@@ -210,91 +208,125 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
 // ---------------------------------------------------------------------------------------------
 // pass 2: gather-form bilinear adjoint, one thread per source texel, block = 32 x 8 texels
 // ---------------------------------------------------------------------------------------------
-struct InversePlan {
-  float a00, a01, a10, a11;     // forward map, pixel space: (ix, iy) = A (j, i) + c
-  float i00, i01, i10, i11;     // A^-1
-  float jcf, icf;               // fractional part of the pre-image of the block centre
-  int JC, IC;                   // integer part
-  float rj, ri;                 // half extents of the pre-image of a texel's (-1,1)^2 support
+// Per-layer inverse placement, computed once per (b, l) by inverse_plans_kernel (double precision)
+// so that the thousands of pass-2 blocks of a layer do not each redo the divisions.
+struct InverseLayer {
+  double i00, i01, i10, i11;    // A^-1, pixel space
+  double c0, c1;                // (ix, iy) = A (j, i) + c
+  float a00, a01, a10, a11;     // A
+  float rj, ri;                 // half extents of the pre-image of a texel's (-1,1)^2 support (+ slack)
+  float r00, r10;               // 1/a00, 1/a10 (0 if ~0): per-row interval refinement for wide windows
   int valid;                    // 0: non-finite or singular placement -> grad_x of this layer is 0
+  int wide;                     // 1: window wider than 4 somewhere -> refine every row
 };
+
+static_assert(sizeof(InverseLayer) <= 128, "workspace reserves 128 B per layer plan");
+
+static __global__ void inverse_plans_kernel(const float* __restrict__ theta, InverseLayer* __restrict__ plans, int n, int H, int W) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const float* th = theta + (long long)k * 6;
+  const double w = W, h = H;
+  const double a00 = th[0], a01 = th[1] * (w / h), a10 = th[3] * (h / w), a11 = th[4];
+  InverseLayer q;
+  q.c0 = a00 * (0.5 - 0.5 * w) + a01 * (0.5 - 0.5 * h) + th[2] * 0.5 * w + 0.5 * (w - 1.0);
+  q.c1 = a10 * (0.5 - 0.5 * w) + a11 * (0.5 - 0.5 * h) + th[5] * 0.5 * h + 0.5 * (h - 1.0);
+  const double inv = 1.0 / (a00 * a11 - a01 * a10);
+  q.i00 = a11 * inv; q.i01 = -a01 * inv; q.i10 = -a10 * inv; q.i11 = a00 * inv;
+  q.a00 = (float)a00; q.a01 = (float)a01; q.a10 = (float)a10; q.a11 = (float)a11;
+  const double rj = fabs(q.i00) + fabs(q.i01), ri = fabs(q.i10) + fabs(q.i11);
+  q.valid = isfinite(q.c0) && isfinite(q.c1) && isfinite(rj) && isfinite(ri) && rj < 1.0e6 && ri < 1.0e6;
+  q.rj = (float)rj * 1.0001f + 1e-3f; q.ri = (float)ri * 1.0001f + 1e-3f;
+  q.r00 = fabs(a00) > 1e-6 ? (float)(1.0 / a00) : 0.f;
+  q.r10 = fabs(a10) > 1e-6 ? (float)(1.0 / a10) : 0.f;
+  q.wide = (2.0 * rj > 3.5) || (2.0 * ri > 3.5);
+  plans[k] = q;
+}
 
 constexpr int kP2W = 32, kP2H = 8;
 
 template <typename T>
 __global__ void __launch_bounds__(kP2W * kP2H)
-render_bwd_pass2(const float* __restrict__ theta, const float2* __restrict__ rec, const float4* __restrict__ gp,
+render_bwd_pass2(const InverseLayer* __restrict__ plans, const float2* __restrict__ rec, const float4* __restrict__ gp,
                  T* __restrict__ gx, Geometry g) {
-  __shared__ InversePlan ip;
+  __shared__ float s_jcf, s_icf;
+  __shared__ int s_JC, s_IC, s_ok;
   const int n = blockIdx.z;                     // b * L + l
   const int b = n / g.L;
   const int x0b = blockIdx.x * kP2W, y0b = blockIdx.y * kP2H;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const InverseLayer& L_ = plans[n];
   if (threadIdx.x == 0) {
-    const float* th = theta + (long long)n * 6;
-    const double w = g.W, h = g.H;
-    const double a00 = th[0], a01 = th[1] * (w / h), a10 = th[3] * (h / w), a11 = th[4];
-    const double c0 = a00 * (0.5 - 0.5 * w) + a01 * (0.5 - 0.5 * h) + th[2] * 0.5 * w + 0.5 * (w - 1.0);
-    const double c1 = a10 * (0.5 - 0.5 * w) + a11 * (0.5 - 0.5 * h) + th[5] * 0.5 * h + 0.5 * (h - 1.0);
-    const double det = a00 * a11 - a01 * a10;
-    InversePlan q;
-    q.a00 = (float)a00; q.a01 = (float)a01; q.a10 = (float)a10; q.a11 = (float)a11;
-    q.valid = 0;
-    const double xc = x0b + 0.5 * kP2W, yc = y0b + 0.5 * kP2H;      // block centre (source space)
-    const double inv = 1.0 / det;
-    const double i00 = a11 * inv, i01 = -a01 * inv, i10 = -a10 * inv, i11 = a00 * inv;
-    const double jc = i00 * (xc - c0) + i01 * (yc - c1), ic = i10 * (xc - c0) + i11 * (yc - c1);
-    const double rj = fabs(i00) + fabs(i01), ri = fabs(i10) + fabs(i11);
-    q.i00 = (float)i00; q.i01 = (float)i01; q.i10 = (float)i10; q.i11 = (float)i11;
-    q.JC = q.IC = 0; q.jcf = q.icf = 0.f; q.rj = q.ri = 0.f;
-    if (isfinite(jc) && isfinite(ic) && isfinite(rj) && isfinite(ri)) {
-      // a block whose pre-image is far outside the output image cannot be touched by any pixel
-      const double far = 4.0 * (w + h) + 64.0 * (rj + ri);
-      if (fabs(jc) < far + 1.0e6 && fabs(ic) < far + 1.0e6 && rj < 1.0e6 && ri < 1.0e6) {
-        const double fj = floor(jc), fi = floor(ic);
-        q.JC = (int)fj; q.IC = (int)fi; q.jcf = (float)(jc - fj); q.icf = (float)(ic - fi);
-        q.rj = (float)rj * 1.0001f + 1e-3f; q.ri = (float)ri * 1.0001f + 1e-3f;
-        q.valid = 1;
-      }
-    }
-    ip = q;
+    // pre-image of the block centre, split into integer + fraction in double precision
+    const double xc = x0b + 0.5 * kP2W - L_.c0, yc = y0b + 0.5 * kP2H - L_.c1;
+    const double jc = L_.i00 * xc + L_.i01 * yc, ic = L_.i10 * xc + L_.i11 * yc;
+    int ok = L_.valid && isfinite(jc) && isfinite(ic) && fabs(jc) < 1.0e8 && fabs(ic) < 1.0e8;
+    const double fj = floor(jc), fi = floor(ic);
+    s_JC = ok ? (int)fj : 0; s_IC = ok ? (int)fi : 0;
+    s_jcf = ok ? (float)(jc - fj) : 0.f; s_icf = ok ? (float)(ic - fi) : 0.f;
+    s_ok = ok;
   }
+  const float a00 = L_.a00, a01 = L_.a01, a10 = L_.a10, a11 = L_.a11;
+  const float i00 = (float)L_.i00, i01 = (float)L_.i01, i10 = (float)L_.i10, i11 = (float)L_.i11;
+  const float rj = L_.rj, ri = L_.ri;
+  const int wide = L_.wide;
   __syncthreads();
   const int x = x0b + tx, y = y0b + ty;
   if (x >= g.W || y >= g.H) return;
   const int hw = g.H * g.W;
   T* gxp = gx + (long long)n * 4 * hw + y * g.W + x;
   float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-  if (ip.valid) {
+  if (s_ok) {
+    const int JC = s_JC, IC = s_IC;
+    const float jcf = s_jcf, icf = s_icf;
     const float dxl = (float)tx - 0.5f * kP2W, dyl = (float)ty - 0.5f * kP2H;   // texel - block centre
     // pre-image of this texel relative to (JC, IC); candidates are the integer points within (rj, ri) of it,
-    // clamped to the output image (all in float first: the window of a near-singular placement is huge)
-    const float pj = ip.jcf + ip.i00 * dxl + ip.i01 * dyl;
-    const float pi = ip.icf + ip.i10 * dxl + ip.i11 * dyl;
-    const float mlo = fmaxf(ceilf(pj - ip.rj), (float)(-ip.JC)), mhi = fminf(floorf(pj + ip.rj), (float)(g.W - 1 - ip.JC));
-    const float nlo = fmaxf(ceilf(pi - ip.ri), (float)(-ip.IC)), nhi = fminf(floorf(pi + ip.ri), (float)(g.H - 1 - ip.IC));
+    // clamped to the output image (in float first: the window of a near-singular placement is huge)
+    const float pj = jcf + i00 * dxl + i01 * dyl;
+    const float pi = icf + i10 * dxl + i11 * dyl;
+    const float mlo = fmaxf(ceilf(pj - rj), (float)(-JC)), mhi = fminf(floorf(pj + rj), (float)(g.W - 1 - JC));
+    const float nlo = fmaxf(ceilf(pi - ri), (float)(-IC)), nhi = fminf(floorf(pi + ri), (float)(g.H - 1 - IC));
     if (mlo <= mhi && nlo <= nhi) {
       const int m0 = (int)mlo, m1 = (int)mhi, n0 = (int)nlo, n1 = (int)nhi;
-      const float2* recn = rec + (long long)n * hw;
-      const float4* gpb = gp + (long long)b * hw;
-      for (int nn = n0; nn <= n1; ++nn) {
-        const float di = (float)nn - ip.icf;
-        const float ub = fmaf(ip.a01, di, -dxl), vb = fmaf(ip.a11, di, -dyl);
-        const int rowoff = (ip.IC + nn) * g.W + ip.JC;
-        for (int mm = m0; mm <= m1; ++mm) {
-          const float dj = (float)mm - ip.jcf;
-          const float u = fmaf(ip.a00, dj, ub), v = fmaf(ip.a10, dj, vb);    // (ix, iy)(candidate) - (x, y)
-          const float wx = 1.f - fabsf(u), wy = 1.f - fabsf(v);
-          if (wx > 0.f && wy > 0.f) {
-            const float wgt = wx * wy;
-            const float2 r = __ldg(recn + rowoff + mm);
-            const float4 G = __ldg(gpb + rowoff + mm);
-            const float wt = wgt * r.x;
-            acc0 = fmaf(wt, G.x, acc0);
-            acc1 = fmaf(wt, G.y, acc1);
-            acc2 = fmaf(wt, G.z, acc2);
-            acc3 = fmaf(wgt, r.y, acc3);
-          }
+      float di = nlo - icf;
+      const float2* recn = rec + (long long)n * hw + ((IC + n0) * g.W + JC);
+      const float4* gpb = gp + (long long)b * hw + ((IC + n0) * g.W + JC);
+      const float dj0 = mlo - jcf;
+      for (int nn = n0; nn <= n1; ++nn, di += 1.f, recn += g.W, gpb += g.W) {
+        const float ub = fmaf(a01, di, -dxl), vb = fmaf(a11, di, -dyl);
+        int ma = m0, mb = m1;
+        float dja = dj0;
+        if (wide) {
+          // magnifying or near-singular placement: the bounding box of a skinny pre-image parallelogram is
+          // mostly empty.  Solve |a00 dj + ub| < 1 and |a10 dj + vb| < 1 for this row (dj = mm - jcf) and
+          // keep one candidate of slack on either side (its weight is 0 anyway).
+          float lo = -3.0e9f, hi = 3.0e9f;
+          if (L_.r00 != 0.f) {
+            const float t0 = (-1.f - ub) * L_.r00, t1 = (1.f - ub) * L_.r00;
+            lo = fmaxf(lo, fminf(t0, t1)); hi = fminf(hi, fmaxf(t0, t1));
+          } else if (fabsf(ub) >= 1.f) { hi = -3.0e9f; }
+          if (L_.r10 != 0.f) {
+            const float t0 = (-1.f - vb) * L_.r10, t1 = (1.f - vb) * L_.r10;
+            lo = fmaxf(lo, fminf(t0, t1)); hi = fminf(hi, fmaxf(t0, t1));
+          } else if (fabsf(vb) >= 1.f) { hi = -3.0e9f; }
+          lo = fmaxf(floorf(lo + jcf) - 1.f, mlo);
+          hi = fminf(ceilf(hi + jcf) + 1.f, mhi);
+          if (!(lo <= hi)) continue;
+          ma = (int)lo; mb = (int)hi;
+          dja = lo - jcf;
+        }
+        float u = fmaf(a00, dja, ub);                                  // (ix, iy)(candidate) - (x, y)
+        float v = fmaf(a10, dja, vb);
+#pragma unroll 1
+        for (int mm = ma; mm <= mb; ++mm, u += a00, v += a10) {
+          const float wgt = fmaxf(1.f - fabsf(u), 0.f) * fmaxf(1.f - fabsf(v), 0.f);   // hat(u) hat(v)
+          const float2 r = __ldg(recn + mm);
+          const float4 G = __ldg(gpb + mm);
+          const float wt = wgt * r.x;
+          acc0 = fmaf(wt, G.x, acc0);
+          acc1 = fmaf(wt, G.y, acc1);
+          acc2 = fmaf(wt, G.z, acc2);
+          acc3 = fmaf(wgt, r.y, acc3);
         }
       }
     }
