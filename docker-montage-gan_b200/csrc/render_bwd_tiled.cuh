@@ -56,10 +56,10 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
   const int hw = g.H * g.W;
   const int j = j0 + tx;
   const int pix0 = (i0 + ty) * g.W + j;                       // pixel k lives 8*k rows further down
-  const int row8 = 8 * g.W;
+  const int row8 = kRowStep * g.W;                          // a thread's pixels are kRowStep rows apart
   bool live[kPx];
 #pragma unroll
-  for (int k = 0; k < kPx; ++k) live[k] = j < g.W && i0 + ty + 8 * k < g.H;
+  for (int k = 0; k < kPx; ++k) live[k] = j < g.W && i0 + ty + kRowStep * k < g.H;
   float2* recb = rec + (long long)b * g.L * hw + pix0;
   const typename SavedAlpha<T>::type* savb = sav + (long long)b * g.L * hw + pix0;
 
@@ -142,7 +142,7 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
       float r_, g_, b_, a;
       float dxr, dxg, dxb, dxa, dyr, dyg, dyb, dya;
       if (mode == kStaged) {
-        const float dif = (float)(ty + 8 * k - kTH / 2);
+        const float dif = (float)(ty + kRowStep * k - kTH / 2);
         const float ix = fmaf(a01, dif, bx), iy = fmaf(a11, dif, by);
         const float fxf = floorf(ix), fyf = floorf(iy);
         const SampleGrad s = sample_staged_grad<T>(buf + (int)fyf * pitch + (int)fxf, pitch, ix - fxf, iy - fyf);
@@ -152,7 +152,7 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
         upk(s.dy_rg, dyr, dyg); upk(s.dy_ba, dyb, dya);
       } else {
         // huge footprint: bounds-checked taps straight from global memory
-        const Taps tp = make_taps(p.aff, tx - kTW / 2, ty + 8 * k - kTH / 2, g.H, g.W, g.sh);
+        const Taps tp = make_taps(p.aff, tx - kTW / 2, ty + kRowStep * k - kTH / 2, g.H, g.W, g.sh);
         const float shift = g.m11 ? 1.f : 0.f;
         float v[4][4], zz[4];
 #pragma unroll
@@ -179,7 +179,7 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
         const float gr = GP0[k] * ta, gg = GP1[k] * ta, gb = GP2[k] * ta;
         const float dix = fmaf(gr, dxr, fmaf(gg, dxg, fmaf(gb, dxb, ga * dxa)));
         const float diy = fmaf(gr, dyr, fmaf(gg, dyg, fmaf(gb, dyb, ga * dya)));
-        const float yi = norm_coord(i0 + ty + 8 * k, g.H);
+        const float yi = norm_coord(i0 + ty + kRowStep * k, g.H);
         accx += dix; accxy = fmaf(dix, yi, accxy);
         accy += diy; accyy = fmaf(diy, yi, accyy);
       }
@@ -218,6 +218,9 @@ struct InverseLayer {
   float r00, r10;               // 1/a00, 1/a10 (0 if ~0): per-row interval refinement for wide windows
   int valid;                    // 0: non-finite or singular placement -> grad_x of this layer is 0
   int wide;                     // 1: window wider than 4 somewhere -> refine every row
+  int shift_only;               // 1: pure translation (a00 = a11 = 1, a01 = a10 = 0 exactly): 2x2 stencil adjoint
+  int X, Y;                     // shift_only: ix = j + X + fx, iy = i + Y + fy
+  float fx, fy;
 };
 
 static_assert(sizeof(InverseLayer) <= 128, "workspace reserves 128 B per layer plan");
@@ -240,6 +243,12 @@ static __global__ void inverse_plans_kernel(const float* __restrict__ theta, Inv
   q.r00 = fabs(a00) > 1e-6 ? (float)(1.0 / a00) : 0.f;
   q.r10 = fabs(a10) > 1e-6 ? (float)(1.0 / a10) : 0.f;
   q.wide = (2.0 * rj > 3.5) || (2.0 * ri > 3.5);
+  // what STNv2c emits (convert_translate_to_2x3, image_utils.py:316-335): the adjoint is a fixed 2x2 stencil
+  q.shift_only = (th[0] == 1.f && th[1] == 0.f && th[3] == 0.f && th[4] == 1.f && isfinite(q.c0) && isfinite(q.c1) &&
+                  fabs(q.c0) < 1.0e8 && fabs(q.c1) < 1.0e8);
+  const double fX = floor(q.c0), fY = floor(q.c1);
+  q.X = q.shift_only ? (int)fX : 0; q.Y = q.shift_only ? (int)fY : 0;
+  q.fx = q.shift_only ? (float)(q.c0 - fX) : 0.f; q.fy = q.shift_only ? (float)(q.c1 - fY) : 0.f;
   plans[k] = q;
 }
 
@@ -256,6 +265,44 @@ render_bwd_pass2(const InverseLayer* __restrict__ plans, const float2* __restric
   const int x0b = blockIdx.x * kP2W, y0b = blockIdx.y * kP2H;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const InverseLayer& L_ = plans[n];
+  if (L_.shift_only) {
+    // pure translation: texel (x, y) is tap (x0 + dx, y0 + dy) of pixel (x - X - dx, y - Y - dy), dx, dy in {0, 1},
+    // with weights (dx ? fx : 1 - fx) (dy ? fy : 1 - fy) -- a fixed 2x2 stencil, uniform over the layer
+    const int x = x0b + tx, y = y0b + ty;
+    if (x >= g.W || y >= g.H) return;
+    const int hw = g.H * g.W;
+    const int j1 = x - L_.X, i1 = y - L_.Y;                   // the pixel for which this texel is tap (0, 0)
+    const float wx0 = 1.f - L_.fx, wx1 = L_.fx, wy0 = 1.f - L_.fy, wy1 = L_.fy;
+    const float2* recn = rec + (long long)n * hw;
+    const float4* gpb = gp + (long long)b * hw;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+      const int i = i1 - dy;
+      if ((unsigned)i >= (unsigned)g.H) continue;
+      const float wy = dy ? wy1 : wy0;
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int j = j1 - dx;
+        if ((unsigned)j >= (unsigned)g.W) continue;
+        const float wgt = wy * (dx ? wx1 : wx0);
+        const float2 r = __ldg(recn + i * g.W + j);
+        const float4 G = __ldg(gpb + i * g.W + j);
+        const float wt = wgt * r.x;
+        acc0 = fmaf(wt, G.x, acc0);
+        acc1 = fmaf(wt, G.y, acc1);
+        acc2 = fmaf(wt, G.z, acc2);
+        acc3 = fmaf(wgt, r.y, acc3);
+      }
+    }
+    const float zs = g.m11 ? 0.5f : 1.f;
+    T* gxp = gx + (long long)n * 4 * hw + y * g.W + x;
+    st(gxp, zs * acc0);
+    st(gxp + hw, zs * acc1);
+    st(gxp + 2 * hw, zs * acc2);
+    st(gxp + 3 * hw, zs * acc3);
+    return;
+  }
   if (threadIdx.x == 0) {
     // pre-image of the block centre, split into integer + fraction in double precision
     const double xc = x0b + 0.5 * kP2W - L_.c0, yc = y0b + 0.5 * kP2H - L_.c1;

@@ -62,10 +62,10 @@ render_fwd_tiled(const T* __restrict__ x, const float* __restrict__ theta, T* __
   const int hw = g.H * g.W;                                   // one plane fits 32 bits (host-checked)
   const int j = j0 + tx;
   const int pix0 = (i0 + ty) * g.W + j;                       // pixel k lives 8*k rows further down
-  const int row8 = 8 * g.W;
+  const int row8 = kRowStep * g.W;                          // a thread's pixels are kRowStep rows apart
   bool live[kPx];
 #pragma unroll
-  for (int k = 0; k < kPx; ++k) live[k] = j < g.W && i0 + ty + 8 * k < g.H;
+  for (int k = 0; k < kPx; ++k) live[k] = j < g.W && i0 + ty + kRowStep * k < g.H;
   const float djf = (float)(tx - kTW / 2);
   float S0[kPx], S1[kPx], S2[kPx], R[kPx];
 #pragma unroll
@@ -97,14 +97,14 @@ render_fwd_tiled(const T* __restrict__ x, const float* __restrict__ theta, T* __
     for (int k = 0; k < kPx; ++k) {
       float r_, g_, b_, a;
       if (mode == kStaged) {
-        const float dif = (float)(ty + 8 * k - kTH / 2);
+        const float dif = (float)(ty + kRowStep * k - kTH / 2);
         const float ix = fmaf(a01, dif, bx), iy = fmaf(a11, dif, by);
         const float fxf = floorf(ix), fyf = floorf(iy);
         const Sample s = sample_staged<T>(buf + (int)fyf * pitch + (int)fxf, pitch, ix - fxf, iy - fyf);
         upk(fma2(s.rg, zs2, zb2), r_, g_);
         upk(fma2(s.ba, zs2, zb2), b_, a);
       } else {
-        const float4 z = sample_pixel_direct<T>(img, p.aff, tx - kTW / 2, ty + 8 * k - kTH / 2, g.H, g.W, g.sh, g.sc,
+        const float4 z = sample_pixel_direct<T>(img, p.aff, tx - kTW / 2, ty + kRowStep * k - kTH / 2, g.H, g.W, g.sh, g.sc,
                                                 g.m11 ? 1.f : 0.f, g.m11 ? 0.5f : 1.f);
         r_ = z.x; g_ = z.y; b_ = z.z; a = z.w;
       }

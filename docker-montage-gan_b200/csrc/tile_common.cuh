@@ -25,8 +25,9 @@ __device__ __forceinline__ f32x2 bc(float a) { return pk(a, a); }
 
 // ---- tile geometry ------------------------------------------------------------------------------
 constexpr int kTW = 32, kTH = 32;           // output tile
-constexpr int kTiledThreads = 256;          // 8 warps; thread (tx, ty) owns pixels (tx, ty + 8k), k = 0..3
-constexpr int kPx = 4;
+constexpr int kTiledThreads = 256;          // 8 warps; thread (tx, ty) owns pixels (tx, ty + kRowStep * k), k < kPx
+constexpr int kPx = kTW * kTH / kTiledThreads;
+constexpr int kRowStep = kTiledThreads / kTW;
 constexpr int kCapTexels = 2816;            // staging capacity (e.g. a 52 x 54 footprint)
 
 enum { kSkip = 0, kStaged = 1, kDirect = 2 };
