@@ -4,6 +4,7 @@
 #include "render_direct.cuh"
 #include "render_bwd_tiled.cuh"
 #include "render_tiled.cuh"
+#include "warp_ops.cuh"
 
 namespace mgr {
 
@@ -136,6 +137,54 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
   return launch_backward<T, false>(x, nullptr, out, gout, nullptr, gx, nullptr, g, flags & MGR_NEED_GRAD_X, s);
 }
 
+// ---- materialised warp and staging helpers (warp_ops.cuh) -----------------------------------------
+template <typename T>
+int launch_warp_forward(const void* x, const float* theta, void* out, const Geometry& g, cudaStream_t s) {
+  dim3 grid((g.W + kTileW - 1) / kTileW, (g.H + kTileH - 1) / kTileH, g.B * g.L);
+  warp_fwd_kernel<T><<<grid, kDirectThreads, 0, s>>>((const T*)x, theta, (T*)out, g);
+  MGR_CUDA(cudaGetLastError());
+  count_launch();
+  return MGR_OK;
+}
+
+template <typename T>
+int launch_warp_backward(const void* x, const float* theta, const void* gout, void* gx, float* gtheta, void* ws,
+                         const Geometry& g, int flags, cudaStream_t s) {
+  const long long n = (long long)g.B * g.L * 4 * g.H * g.W;
+  const bool nx = flags & MGR_NEED_GRAD_X, nt = flags & MGR_NEED_GRAD_THETA;
+  float* gx32 = nullptr;
+  if (nx) {
+    gx32 = (sizeof(T) == 4) ? (float*)gx : (float*)ws;
+    MGR_CUDA(cudaMemsetAsync(gx32, 0, sizeof(float) * n, s));
+  }
+  if (nt) MGR_CUDA(cudaMemsetAsync(gtheta, 0, sizeof(float) * 6 * g.B * g.L, s));
+  dim3 grid((g.W + kTileW - 1) / kTileW, (g.H + kTileH - 1) / kTileH, g.B * g.L);
+  if (nx && nt) warp_bwd_kernel<T, true, true><<<grid, kDirectThreads, 0, s>>>((const T*)x, theta, (const T*)gout, gx32, gtheta, g);
+  else if (nx) warp_bwd_kernel<T, true, false><<<grid, kDirectThreads, 0, s>>>((const T*)x, theta, (const T*)gout, gx32, gtheta, g);
+  else if (nt) warp_bwd_kernel<T, false, true><<<grid, kDirectThreads, 0, s>>>((const T*)x, theta, (const T*)gout, gx32, gtheta, g);
+  MGR_CUDA(cudaGetLastError());
+  count_launch();
+  if (nx && sizeof(T) != 4) {
+    const long long blocks = (n + 255) / 256;
+    cast_from_f32<T><<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, s>>>(gx32, (T*)gx, n);
+    MGR_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  return MGR_OK;
+}
+
+template <typename T>
+int launch_pad_stack(const void* src, const long long* ss, void* dst, int B, int L, int l, int h, int w, int H, int W,
+                     float pad, cudaStream_t s) {
+  const long long total = (long long)B * 4 * H * W;
+  const long long blocks = (total + 255) / 256;
+  pad_stack_kernel<T><<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, s>>>(
+      (const T*)src, ss[0], ss[1], ss[2], ss[3], (T*)dst, B, L, l, h, w, H, W, pad);
+  MGR_CUDA(cudaGetLastError());
+  count_launch();
+  return MGR_OK;
+}
+
 }  // namespace mgr
 
 #include "launchers_decl.h"
@@ -147,4 +196,15 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
   int mgr_bwd_##SUFFIX(const void* x, const float* theta, const void* out, const void* gout, const void* sav, \
                        void* gx, float* gtheta, void* ws, const mgr::Geometry& g, int flags, cudaStream_t s) { \
     return mgr::backward_typed<T>(x, theta, out, gout, sav, gx, gtheta, ws, g, flags, s);                    \
+  }                                                                                                          \
+  int mgr_warp_fwd_##SUFFIX(const void* x, const float* theta, void* out, const mgr::Geometry& g, cudaStream_t s) { \
+    return mgr::launch_warp_forward<T>(x, theta, out, g, s);                                                 \
+  }                                                                                                          \
+  int mgr_warp_bwd_##SUFFIX(const void* x, const float* theta, const void* gout, void* gx, float* gtheta,    \
+                            void* ws, const mgr::Geometry& g, int flags, cudaStream_t s) {                   \
+    return mgr::launch_warp_backward<T>(x, theta, gout, gx, gtheta, ws, g, flags, s);                        \
+  }                                                                                                          \
+  int mgr_pad_stack_##SUFFIX(const void* src, const long long* ss, void* dst, int B, int L, int l, int h,    \
+                             int w, int H, int W, float pad, cudaStream_t s) {                               \
+    return mgr::launch_pad_stack<T>(src, ss, dst, B, L, l, h, w, H, W, pad, s);                              \
   }

@@ -8,6 +8,7 @@
 #include "montage_render.h"
 #include "mgr_common.cuh"
 #include "mgr_errors.h"
+#include "warp_ops.cuh"
 
 #include "launchers_decl.h"
 
@@ -134,6 +135,78 @@ int mgr_render_backward(const void* x, const int64_t* x_strides, const float* th
     case MGR_F32: return mgr_bwd_f32(x, theta, out, grad_out, saved_alpha, grad_x, grad_theta, workspace, g, flags, s);
     case MGR_BF16: return mgr_bwd_bf16(x, theta, out, grad_out, saved_alpha, grad_x, grad_theta, workspace, g, flags, s);
     default: return mgr_bwd_f16(x, theta, out, grad_out, saved_alpha, grad_x, grad_theta, workspace, g, flags, s);
+  }
+}
+
+
+int mgr_warp_forward(const void* x, const int64_t* x_strides, const float* theta, void* out, int B, int L, int H,
+                     int W, int dtype, int range_mode, void* stream) {
+  mgr::Geometry g;
+  if (int rc = check_common(x, x_strides, B, L, H, W, dtype, range_mode, &g)) return rc;
+  if (!theta || !out) return fail(MGR_ERR_INVALID_ARGUMENT, "theta / out is NULL");
+  if (B == 0) return MGR_OK;
+  if ((long long)B * L > 65535) return fail(MGR_ERR_UNSUPPORTED, "B*L=%lld exceeds 65535 per call", (long long)B * L);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case MGR_F32: return mgr_warp_fwd_f32(x, theta, out, g, s);
+    case MGR_BF16: return mgr_warp_fwd_bf16(x, theta, out, g, s);
+    default: return mgr_warp_fwd_f16(x, theta, out, g, s);
+  }
+}
+
+size_t mgr_warp_backward_workspace_bytes(int B, int L, int H, int W, int dtype, int flags) {
+  if (B <= 0 || L <= 0 || H <= 0 || W <= 0) return 0;
+  if ((flags & MGR_NEED_GRAD_X) && dtype != MGR_F32) return sizeof(float) * (size_t)B * L * 4 * H * W;
+  return 0;
+}
+
+int mgr_warp_backward(const void* x, const int64_t* x_strides, const float* theta, const void* grad_out,
+                      void* grad_x, float* grad_theta, void* workspace, size_t workspace_bytes, int B, int L, int H,
+                      int W, int dtype, int range_mode, int flags, void* stream) {
+  mgr::Geometry g;
+  if (int rc = check_common(x, x_strides, B, L, H, W, dtype, range_mode, &g)) return rc;
+  if (!theta || !grad_out) return fail(MGR_ERR_INVALID_ARGUMENT, "theta / grad_out is NULL");
+  if ((flags & MGR_NEED_GRAD_X) && !grad_x) return fail(MGR_ERR_INVALID_ARGUMENT, "grad_x is NULL but requested");
+  if ((flags & MGR_NEED_GRAD_THETA) && !grad_theta)
+    return fail(MGR_ERR_INVALID_ARGUMENT, "grad_theta is NULL but requested");
+  if (!(flags & (MGR_NEED_GRAD_X | MGR_NEED_GRAD_THETA)) || B == 0) return MGR_OK;
+  if ((long long)B * L > 65535) return fail(MGR_ERR_UNSUPPORTED, "B*L=%lld exceeds 65535 per call", (long long)B * L);
+  const size_t need = mgr_warp_backward_workspace_bytes(B, L, H, W, dtype, flags);
+  if (need > 0 && (!workspace || workspace_bytes < need))
+    return fail(MGR_ERR_WORKSPACE_TOO_SMALL, "workspace %zu bytes < required %zu", workspace_bytes, need);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case MGR_F32: return mgr_warp_bwd_f32(x, theta, grad_out, grad_x, grad_theta, workspace, g, flags, s);
+    case MGR_BF16: return mgr_warp_bwd_bf16(x, theta, grad_out, grad_x, grad_theta, workspace, g, flags, s);
+    default: return mgr_warp_bwd_f16(x, theta, grad_out, grad_x, grad_theta, workspace, g, flags, s);
+  }
+}
+
+int mgr_translation_to_theta(const float* translation, float* theta, long long n, void* stream) {
+  if (n < 0) return fail(MGR_ERR_INVALID_ARGUMENT, "n=%lld", n);
+  if (n == 0) return MGR_OK;
+  if (!translation || !theta) return fail(MGR_ERR_INVALID_ARGUMENT, "translation / theta is NULL");
+  mgr::translation_to_theta_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(translation, theta, n);
+  MGR_CUDA(cudaGetLastError());
+  mgr::count_launch();
+  return MGR_OK;
+}
+
+int mgr_pad_stack_layer(const void* src, const int64_t* src_strides, void* dst, int B, int L, int l, int h, int w,
+                        int H, int W, float pad_value, int dtype, void* stream) {
+  if (!src || !dst) return fail(MGR_ERR_INVALID_ARGUMENT, "src / dst is NULL");
+  if (B < 0 || L < 1 || l < 0 || l >= L || h < 1 || w < 1 || H < h || W < w)
+    return fail(MGR_ERR_INVALID_ARGUMENT, "bad shape B=%d L=%d l=%d h=%d w=%d H=%d W=%d", B, L, l, h, w, H, W);
+  if (dtype != MGR_F32 && dtype != MGR_BF16 && dtype != MGR_F16) return fail(MGR_ERR_INVALID_ARGUMENT, "bad dtype %d", dtype);
+  if (B == 0) return MGR_OK;
+  long long ss[4];
+  if (src_strides) { for (int k = 0; k < 4; ++k) ss[k] = src_strides[k]; }
+  else { ss[3] = 1; ss[2] = w; ss[1] = (long long)h * w; ss[0] = 4 * ss[1]; }
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case MGR_F32: return mgr_pad_stack_f32(src, ss, dst, B, L, l, h, w, H, W, pad_value, s);
+    case MGR_BF16: return mgr_pad_stack_bf16(src, ss, dst, B, L, l, h, w, H, W, pad_value, s);
+    default: return mgr_pad_stack_f16(src, ss, dst, B, L, l, h, w, H, W, pad_value, s);
   }
 }
 

@@ -1,0 +1,130 @@
+// The callers either side of the fused renderer:
+//   * materialised warp of every layer  -- what STNv2c / STNv2b return to their callers
+//     (fukuwarai/networks.py:250-257, 219-225) and what random_position computes
+//     (custom_utils/image_utils.py:281-294): snapshot / EMA / metrics paths still want the warped
+//     layers themselves;
+//   * translation -> 2x3 theta (image_utils.py:316-335, a B*L Python loop of tiny H2D copies there);
+//   * centre-pad one generator output into the [B,L,4,H,W] canvas (image_utils.py:216-243).
+// These are streaming / gather kernels off the critical path; they share the placement arithmetic
+// of the renderer (mgr_common.cuh) so that warp() followed by a composite equals render().
+#pragma once
+#include "render_direct.cuh"
+
+namespace mgr {
+
+// ---- warp forward: one thread per output pixel of one layer ------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kDirectThreads)
+warp_fwd_kernel(const T* __restrict__ x, const float* __restrict__ theta, T* __restrict__ out, Geometry g) {
+  __shared__ TileAffine aff;
+  const int n = blockIdx.z;                      // b * L + l
+  const int b = n / g.L, l = n - b * g.L;
+  const int j0 = blockIdx.x * kTileW, i0 = blockIdx.y * kTileH;
+  const int dj = threadIdx.x % kTileW, di = threadIdx.x / kTileW;
+  if (threadIdx.x == 0) aff = make_tile_affine(theta + (long long)n * 6, g.H, g.W, j0, i0);
+  __syncthreads();
+  const int j = j0 + dj, i = i0 + di;
+  if (j >= g.W || i >= g.H) return;
+  const float shift = g.m11 ? 1.f : 0.f;
+  const T* img = x + (long long)b * g.sb + (long long)l * g.sl;
+  const Taps p = make_taps(aff, dj, di, g.H, g.W, g.sh);
+  float z[4];
+  sample_rgba(img, g.sc, p, shift, 1.f, z);      // sum_k w_k (x_k + shift), zeros padding
+  const long long hw = (long long)g.H * g.W;
+  T* q = out + (long long)n * 4 * hw + (long long)i * g.W + j;
+#pragma unroll
+  for (int c = 0; c < 4; ++c) st(q + c * hw, z[c] - shift);   // STNv2c: grid_sample(x + 1) - 1
+}
+
+// ---- warp backward: scatter to grad_x (fp32 atomics) and reduce grad_theta ------------------------
+template <typename T, bool kNeedX, bool kNeedTheta>
+__global__ void __launch_bounds__(kDirectThreads)
+warp_bwd_kernel(const T* __restrict__ x, const float* __restrict__ theta, const T* __restrict__ gout,
+                float* __restrict__ gx32, float* __restrict__ gtheta, Geometry g) {
+  __shared__ TileAffine aff;
+  __shared__ float acc[6];
+  const int n = blockIdx.z;
+  const int b = n / g.L, l = n - b * g.L;
+  const int j0 = blockIdx.x * kTileW, i0 = blockIdx.y * kTileH;
+  const int dj = threadIdx.x % kTileW, di = threadIdx.x / kTileW;
+  if (threadIdx.x == 0) aff = make_tile_affine(theta + (long long)n * 6, g.H, g.W, j0, i0);
+  if (threadIdx.x < 6) acc[threadIdx.x] = 0.f;
+  __syncthreads();
+  const int j = j0 + dj, i = i0 + di;
+  const bool live = j < g.W && i < g.H;
+  const long long hw = (long long)g.H * g.W;
+  float part[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (live) {
+    const float shift = g.m11 ? 1.f : 0.f;
+    const T* img = x + (long long)b * g.sb + (long long)l * g.sl;
+    const Taps p = make_taps(aff, dj, di, g.H, g.W, g.sh);
+    const float ex = 1.f - p.fx, ey = 1.f - p.fy;
+    float dix = 0.f, diy = 0.f;
+    const T* go = gout + (long long)n * 4 * hw + (long long)i * g.W + j;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float gc = ld(go + c * hw);
+      if (kNeedX) {
+        float* q = gx32 + ((long long)n * 4 + c) * hw + (long long)p.y0 * g.W + p.x0;
+        if (p.mask & 1u) atomicAdd(q, gc * p.w00);
+        if (p.mask & 2u) atomicAdd(q + 1, gc * p.w01);
+        if (p.mask & 4u) atomicAdd(q + g.W, gc * p.w10);
+        if (p.mask & 8u) atomicAdd(q + g.W + 1, gc * p.w11);
+      }
+      if (kNeedTheta) {
+        const T* pl = img + c * g.sc;
+        const float v00 = (p.mask & 1u) ? ld(pl + p.o00) + shift : 0.f;
+        const float v01 = (p.mask & 2u) ? ld(pl + p.o01) + shift : 0.f;
+        const float v10 = (p.mask & 4u) ? ld(pl + p.o10) + shift : 0.f;
+        const float v11 = (p.mask & 8u) ? ld(pl + p.o11) + shift : 0.f;
+        dix = fmaf(gc, (v01 - v00) * ey + (v11 - v10) * p.fy, dix);
+        diy = fmaf(gc, (v10 - v00) * ex + (v11 - v01) * p.fx, diy);
+      }
+    }
+    if (kNeedTheta) {
+      const float ggx = dix * (0.5f * g.W), ggy = diy * (0.5f * g.H);
+      const float xj = norm_coord(j, g.W), yi = norm_coord(i, g.H);
+      part[0] = ggx * xj; part[1] = ggx * yi; part[2] = ggx;
+      part[3] = ggy * xj; part[4] = ggy * yi; part[5] = ggy;
+    }
+  }
+  if (kNeedTheta) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const float s = warp_sum(part[k]);
+      if ((threadIdx.x & 31) == 0) atomicAdd(&acc[k], s);
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) atomicAdd(gtheta + (long long)n * 6 + threadIdx.x, acc[threadIdx.x]);
+  }
+}
+
+// ---- translation [n,2] -> theta [n,2,3] = [[1,0,dx],[0,1,dy]] --------------------------------------
+static __global__ void translation_to_theta_kernel(const float* __restrict__ tr, float* __restrict__ theta, long long n) {
+  const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const float dx = tr[2 * k], dy = tr[2 * k + 1];
+  float* t = theta + 6 * k;
+  t[0] = 1.f; t[1] = 0.f; t[2] = dx;
+  t[3] = 0.f; t[4] = 1.f; t[5] = dy;
+}
+
+// ---- centre-pad one layer's generator output [B,4,h,w] into the canvas dst[:, l] of [B,L,4,H,W] ----
+template <typename T>
+__global__ void pad_stack_kernel(const T* __restrict__ src, long long ssb, long long ssc, long long ssh, long long ssw,
+                                 T* __restrict__ dst, int B, int L, int l, int h, int w, int H, int W, float pad) {
+  const int top = (H - h) / 2, left = (W - w) / 2;            // pad_256: pad_x1 = pad_x // 2 (image_utils.py:222-225)
+  const long long total = (long long)B * 4 * H * W;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(k % W);
+    const int Y = (int)((k / W) % H);
+    const int c = (int)((k / ((long long)W * H)) % 4);
+    const int b = (int)(k / ((long long)W * H * 4));
+    const int y = Y - top, xx = X - left;
+    T* q = dst + ((((long long)b * L + l) * 4 + c) * H + Y) * W + X;
+    if ((unsigned)y < (unsigned)h && (unsigned)xx < (unsigned)w) *q = src[b * ssb + c * ssc + y * ssh + xx * ssw];
+    else st(q, pad);
+  }
+}
+
+}  // namespace mgr

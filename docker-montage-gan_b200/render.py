@@ -137,3 +137,132 @@ def alpha_composite_pytorch(blchw_lchw: torch.Tensor, use_premultiplied: bool = 
     if blchw_lchw.dim() == 4:
         return render(blchw_lchw.unsqueeze(0), None, in_range="01")[0]
     return render(blchw_lchw, None, in_range="01")
+
+
+# --------------------------------------------------------------------------------------------------
+# materialised warp and the caller-side helpers (rows a4, a10, a12)
+# --------------------------------------------------------------------------------------------------
+class _Warp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, theta, in_range):
+        lib = _lib.load()
+        B, L, _, H, W = x.shape
+        xk, strides = _x_arg(x.detach())
+        th = theta.detach().to(torch.float32).contiguous()
+        out = torch.empty((B, L, 4, H, W), dtype=x.dtype, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.mgr_warp_forward(_ptr(xk), strides, _ptr(th), _ptr(out), B, L, H, W, _DTYPES[x.dtype],
+                                      _RANGES[in_range], _stream_ptr(x.device))
+        _lib.check(rc, "mgr_warp_forward")
+        ctx.in_range, ctx.theta_dtype, ctx.x_strides = in_range, theta.dtype, strides
+        ctx.save_for_backward(xk, th)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, grad_out):
+        lib = _lib.load()
+        xk, th = ctx.saved_tensors
+        B, L, _, H, W = xk.shape
+        need_x, need_t = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        flags = (_lib.MGR_NEED_GRAD_X if need_x else 0) | (_lib.MGR_NEED_GRAD_THETA if need_t else 0)
+        if flags == 0:
+            return None, None, None
+        go = grad_out.to(xk.dtype).contiguous()
+        gx = torch.empty((B, L, 4, H, W), dtype=xk.dtype, device=xk.device) if need_x else None
+        gt = torch.empty((B, L, 2, 3), dtype=torch.float32, device=xk.device) if need_t else None
+        dt = _DTYPES[xk.dtype]
+        ws_bytes = lib.mgr_warp_backward_workspace_bytes(B, L, H, W, dt, flags)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xk.device) if ws_bytes else None
+        with torch.cuda.device(xk.device):
+            rc = lib.mgr_warp_backward(_ptr(xk), ctx.x_strides, _ptr(th), _ptr(go), _ptr(gx), _ptr(gt), _ptr(ws), ws_bytes,
+                                       B, L, H, W, dt, _RANGES[ctx.in_range], flags, _stream_ptr(xk.device))
+        _lib.check(rc, "mgr_warp_backward")
+        if gt is not None and ctx.theta_dtype != torch.float32:
+            gt = gt.to(ctx.theta_dtype)
+        return gx, gt, None
+
+
+def warp(x: torch.Tensor, theta: torch.Tensor, *, in_range: str = "m11") -> torch.Tensor:
+    """Materialised warp of every layer: what ``STNv2c.forward`` returns as its first output
+    (``fukuwarai/networks.py:250-257``; ``in_range='01'`` is the ``STNv2b`` / ``random_position`` form).
+    ``render(x, theta) == composite(warp(x, theta))`` up to rounding."""
+    if theta is None:
+        raise ValueError("warp needs theta")
+    _check_inputs(x, theta, in_range)
+    return _Warp.apply(x, theta, in_range)
+
+
+class _TranslationToTheta(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, translation):
+        lib = _lib.load()
+        tr = translation.detach().to(torch.float32).contiguous()
+        theta = torch.empty(tr.shape[:-1] + (2, 3), dtype=torch.float32, device=tr.device)
+        with torch.cuda.device(tr.device):
+            rc = lib.mgr_translation_to_theta(_ptr(tr), _ptr(theta), tr.numel() // 2, _stream_ptr(tr.device))
+        _lib.check(rc, "mgr_translation_to_theta")
+        ctx.in_dtype = translation.dtype
+        return theta
+
+    @staticmethod
+    def backward(ctx, grad_theta):
+        return grad_theta[..., 2].to(ctx.in_dtype)
+
+
+def convert_translate_to_2x3(translation_bl2_l2: torch.Tensor) -> torch.Tensor:
+    """Drop-in for ``custom_utils.image_utils.convert_translate_to_2x3`` (``:316-335``): [...,2] (dx, dy)
+    -> [...,2,3], one kernel instead of a B*L Python loop of host-to-device copies."""
+    if translation_bl2_l2.shape[-1] != 2:
+        raise ValueError(f"translation must end in a dimension of 2, got {tuple(translation_bl2_l2.shape)}")
+    if not translation_bl2_l2.is_cuda:
+        raise _lib.MontageRenderError("translation must be a CUDA tensor: no CPU path")
+    return _TranslationToTheta.apply(translation_bl2_l2)
+
+
+def random_position(blchw: torch.Tensor, generator: torch.Generator | None = None) -> torch.Tensor:
+    """Drop-in for ``custom_utils.image_utils.random_position`` (``:281-294``): every layer moved by a
+    translation drawn from U(-1, 1); input in [0,1]."""
+    B, L = blchw.shape[:2]
+    tr = torch.empty((B, L, 2), device=blchw.device).uniform_(-1.0, 1.0, generator=generator)
+    return warp(blchw, convert_translate_to_2x3(tr), in_range="01")
+
+
+def make_batch_for_pos_estimator(list_of_bchw, pad_value=0, canvas=(256, 256)) -> torch.Tensor:
+    """Drop-in for ``custom_utils.image_utils.make_batch_for_pos_estimator`` (``:229-243``): the L local
+    generator outputs [B,4,h_l,w_l] are centre-padded to the canvas (256x256 in the reference,
+    ``pad_256`` ``:216-226``) and written straight into one [B,L,4,H,W] tensor -- no per-sample F.pad
+    loop, no stack/transpose/contiguous copies.  Differentiable (the backward is a crop)."""
+    return _PadStack.apply(float(pad_value), tuple(canvas), *list_of_bchw)
+
+
+class _PadStack(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pad_value, canvas, *layers):
+        lib = _lib.load()
+        if not layers:
+            raise ValueError("need at least one layer")
+        H, W = canvas
+        B, dtype, device = layers[0].shape[0], layers[0].dtype, layers[0].device
+        L = len(layers)
+        out = torch.empty((B, L, 4, H, W), dtype=dtype, device=device)
+        ctx.boxes = []
+        with torch.cuda.device(device):
+            for l, t in enumerate(layers):
+                if t.dim() != 4 or t.shape[0] != B or t.shape[1] != 4 or t.dtype != dtype or t.device != device:
+                    raise ValueError(f"layer {l}: expected [B={B},4,h,w] {dtype} on {device}, got {tuple(t.shape)} {t.dtype}")
+                h, w = t.shape[2:]
+                if h > H or w > W:
+                    raise ValueError(f"layer {l} ({h}x{w}) is larger than the canvas {H}x{W}")
+                td = t.detach()
+                strides = (ctypes.c_int64 * 4)(*td.stride())
+                rc = lib.mgr_pad_stack_layer(_ptr(td), strides, _ptr(out), B, L, l, h, w, H, W, pad_value,
+                                             _DTYPES[dtype], _stream_ptr(device))
+                _lib.check(rc, "mgr_pad_stack_layer")
+                ctx.boxes.append(((H - h) // 2, (W - w) // 2, h, w))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad):
+        grads = [grad[:, l, :, top:top + h, left:left + w] for l, (top, left, h, w) in enumerate(ctx.boxes)]
+        return (None, None, *grads)

@@ -117,6 +117,39 @@ int mgr_render_backward(const void* x, const int64_t* x_strides, const float* th
                         int B, int L, int H, int W, int dtype, int range_mode, int flags,
                         void* stream);
 
+/*
+ * Materialised warp of every layer: out[b,l] = warp(x[b,l], theta[b,l]), [B,L,4,H,W] contiguous.
+ *   replaces: the warp lines of STNv2c.forward (fukuwarai/networks.py:250-257, MGR_RANGE_M11: the
+ *   "+1, grid_sample, -1" form) and of STNv2b.forward / random_position (networks.py:219-225,
+ *   custom_utils/image_utils.py:289-294, MGR_RANGE_01).  Kept for the callers that consume warped
+ *   layers themselves (EMA snapshots, metrics); the training path uses mgr_render_forward instead.
+ */
+int mgr_warp_forward(const void* x, const int64_t* x_strides, const float* theta, void* out, int B,
+                     int L, int H, int W, int dtype, int range_mode, void* stream);
+size_t mgr_warp_backward_workspace_bytes(int B, int L, int H, int W, int dtype, int flags);
+/* grad_out [B,L,4,H,W] contiguous; grad_x / grad_theta written completely (see mgr_render_backward). */
+int mgr_warp_backward(const void* x, const int64_t* x_strides, const float* theta,
+                      const void* grad_out, void* grad_x, float* grad_theta, void* workspace,
+                      size_t workspace_bytes, int B, int L, int H, int W, int dtype, int range_mode,
+                      int flags, void* stream);
+
+/*
+ * translation [n,2] (dx, dy) -> theta [n,2,3] = [[1,0,dx],[0,1,dy]], one launch.
+ *   replaces: convert_translate_to_2x3 (custom_utils/image_utils.py:316-335), a B*L Python loop that
+ *   builds one torch.tensor(device=...) per layer.  Backward is a slice (grad_theta[..., 2]).
+ */
+int mgr_translation_to_theta(const float* translation, float* theta, long long n, void* stream);
+
+/*
+ * Centre-pad one local generator's output src [B,4,h,w] into layer l of dst [B,L,4,H,W]
+ * (constant pad_value outside), one launch per layer.
+ *   replaces: pad_256 + make_batch_for_pos_estimator (custom_utils/image_utils.py:216-243), a
+ *   per-sample F.pad loop followed by stack + transpose + contiguous.  src_strides: element strides
+ *   [b,c,h,w] or NULL for contiguous.  Backward is a crop (a view).
+ */
+int mgr_pad_stack_layer(const void* src, const int64_t* src_strides, void* dst, int B, int L, int l,
+                        int h, int w, int H, int W, float pad_value, int dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -263,3 +263,106 @@ def test_tiled_kernels_match_direct_kernels(dtype, tf):
         # grad_theta sums +-terms over all pixels: two fp32 evaluation orders differ by more than one of them
         # differs from fp64 (the three-way tests above bound that); this is only a gross-consistency check
         assert rel_err(res[0][2], res[1][2]) <= (2e-3 if dtype == torch.float32 else 5e-2)
+
+
+# --------------------------------------------------------------------------------------------------
+# callers either side of the renderer: warp, theta builder, pad+stack, modules
+# --------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("in_range", ["m11", "01"])
+@pytest.mark.parametrize("tf", ["I", "T"])
+def test_warp_matches_oracle(in_range, tf):
+    B, L, H, W = 2, 5, 40, 48
+    x = synth.make_layers(B, L, H, W, "W", seed=8)
+    if in_range == "01":
+        x = (x + 1) / 2
+    th = synth.make_theta(B, L, tf, seed=8)
+    gw = torch.randn(B, L, 4, H, W, generator=torch.Generator().manual_seed(8))
+    xd, td = x.to(DEV).requires_grad_(True), th.to(DEV).requires_grad_(True)
+    w = mr.warp(xd, td, in_range=in_range)
+    w.backward(gw.to(DEV))
+    for dt in (np.float32, np.float64):
+        ref, aux = R.warp_fwd(x.numpy(), th.numpy(), in_range, dt)
+        gimg, ggx, ggy = R.grid_sample_bwd((B * L, 4, H, W), aux, gw.numpy().astype(dt).reshape(B * L, 4, H, W))
+        gth = R.affine_grid_bwd(ggx, ggy, dt).reshape(B, L, 2, 3)
+        if dt == np.float64:
+            assert max_abs(w.detach().cpu().numpy(), ref) < FWD_TOL
+            assert rel_err(xd.grad.cpu().numpy(), gimg.reshape(x.shape)) < GRAD_TOL
+            assert rel_err(td.grad.cpu().numpy(), gth) < 5e-4
+
+
+def test_warp_then_composite_equals_render():
+    B, L, H, W = 2, 6, 64, 64
+    x = synth.make_layers(B, L, H, W, "S", seed=12).to(DEV)
+    th = synth.make_theta(B, L, "I", seed=12).to(DEV)
+    a = mr.render(x, th)
+    b = mr.render(mr.warp(x, th), None)
+    assert (a - b).abs().max().item() < 1e-5
+
+
+def test_translation_theta_and_known_answers(golden):
+    tr = torch.from_numpy(golden["ka/translate2x3/in"]).to(DEV).requires_grad_(True)
+    th = mr.convert_translate_to_2x3(tr)
+    assert np.array_equal(th.detach().cpu().numpy(), golden["ka/translate2x3/out"])
+    th.backward(torch.arange(th.numel(), dtype=torch.float32, device=DEV).view_as(th))
+    assert torch.equal(tr.grad, torch.tensor([[[2., 5.], [8., 11.]]], device=DEV))
+    # +tx moves content left (image_utils.py:23-28)
+    w = mr.warp(torch.from_numpy(golden["ka/shift/in"]).to(DEV), torch.from_numpy(golden["ka/shift/theta"]).to(DEV), in_range="01")
+    assert max_abs(w[0].cpu().numpy(), golden["ka/shift/out"]) < 1e-6
+    assert w[0, 0, 0, 4].argmax().item() == 3
+
+
+def test_random_position_is_a_translation_warp():
+    x = (synth.make_layers(2, 3, 32, 32, "F", seed=1) + 1) / 2
+    g = torch.Generator(device=DEV).manual_seed(0)
+    y = mr.random_position(x.to(DEV), generator=g)
+    assert y.shape == x.shape and y.min() >= 0 and y.max() <= 1 + 1e-6
+
+
+def test_make_batch_for_pos_estimator_matches_reference_padding():
+    import torch.nn.functional as F
+    B = 3
+    sizes = [(256, 256), (160, 224), (96, 160), (64, 96), (64, 32)]       # custom/dataset_aio.py:30-83
+    g = torch.Generator().manual_seed(4)
+    layers = [torch.rand(B, 4, h, w, generator=g) * 2 - 1 for h, w in sizes]
+    dev_layers = [t.to(DEV).requires_grad_(True) for t in layers]
+    out = mr.make_batch_for_pos_estimator(dev_layers, pad_value=-1)
+    assert out.shape == (B, len(sizes), 4, 256, 256)
+    for l, t in enumerate(layers):                                          # pad_256, image_utils.py:216-226
+        h, w = t.shape[2:]
+        px, py = 256 - w, 256 - h
+        ref = F.pad(t, (px // 2, px - px // 2, py // 2, py - py // 2), value=-1.0)
+        assert torch.equal(out[:, l].cpu(), ref)
+    gout = torch.randn(out.shape, generator=g).to(DEV)
+    out.backward(gout)
+    for l, t in enumerate(dev_layers):
+        h, w = t.shape[2:]
+        top, left = (256 - h) // 2, (256 - w) // 2
+        assert torch.equal(t.grad, gout[:, l, :, top:top + h, left:left + w])
+
+
+def test_modules_drop_in():
+    from montage_gan_b200 import modules as M
+    torch.manual_seed(0)
+    B, L, R_ = 2, 3, 128
+    x = synth.make_layers(B, L, R_, R_, "S", seed=3).to(DEV)
+    stn = M.STNv2c(R_, 4, L).to(DEV)
+    warped, theta = stn(x)
+    assert warped.shape == x.shape and theta.shape == (B, L, 2, 3)
+    eye = torch.eye(2, 3, device=DEV).expand(B, L, 2, 3)
+    assert torch.equal(theta, eye)                    # identity at init (networks.py:201-203)
+    assert (warped - x).abs().max().item() < 1e-6
+    ren = M.AnalyticRenderer(R_, 4, L).to(DEV)
+    assert len(list(ren.parameters())) == 0 and ren.state_dict() == {}
+    out = ren(warped)
+    assert out.shape == (B, 4, R_, R_)
+    # fused path: same result, one kernel
+    stn_f = M.STNv2c(R_, 4, L, fused=True).to(DEV)
+    stn_f.load_state_dict(stn.state_dict())
+    xf, tf_ = stn_f(x)
+    assert (M.FusedRenderer(R_, 4, L)(xf, tf_) - out).abs().max().item() < 1e-5
+    # gradients reach the placement net through grad_theta
+    with torch.no_grad():
+        stn.fc_loc[2].bias.normal_(0, 0.2)
+    w2, t2 = stn(x)
+    ren(w2).square().mean().backward()
+    assert stn.fc_loc[2].bias.grad.abs().sum().item() > 0
