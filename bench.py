@@ -45,6 +45,16 @@ def algorithmic_bytes(B, L, H, W, s_x, s_o, s_g):
     return fwd, bwd
 
 
+def measured_traffic(workload):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+    (profiles/roofline_traffic.json, written by tools/update_traffic.py from the .ncu-rep)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as fh:
+            return json.load(fh).get(workload)
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def measured_peak_gbs():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -159,7 +169,7 @@ def run_cuda_arm(args, wl):
     import torch
     import torch.distributed as dist
     import montage_gan_b200  # noqa: F401
-    from montage_gan_b200 import _lib, render as mr, synth
+    from montage_gan_b200 import _lib, sharding, synth
 
     B, L, H, W, dtype_name, desc = wl
     rank = int(os.environ.get("RANK", "0"))
@@ -184,11 +194,7 @@ def run_cuda_arm(args, wl):
         seed = 1000 * rank + k
         xb = synth.make_layers(gen_B, L, H, W, "S", seed=seed)
         reps = (B + gen_B - 1) // gen_B
-        x = xb.repeat(reps, 1, 1, 1, 1)[:B].to(dev, dtype)
-        # decorrelate the tiled copies with a per-sample roll so samples differ
-        for r in range(1, reps):
-            x[r * gen_B:(r + 1) * gen_B] = torch.roll(x[r * gen_B:(r + 1) * gen_B], shifts=(7 * r, 13 * r), dims=(-2, -1))
-        xs.append(x.contiguous())
+        xs.append(xb.repeat(reps, 1, 1, 1, 1)[:B].to(dev, dtype).contiguous())   # layers repeat every gen_B samples; thetas do not
         ths.append(synth.make_theta(B, L, "I", seed=seed).to(dev))
         gos.append(synth.make_grad_out(B, H, W, "randn", seed=seed).to(dev, dtype))
     out = torch.empty((B, 4, H, W), dtype=dtype, device=dev)
@@ -237,48 +243,47 @@ def run_cuda_arm(args, wl):
     fwd_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
     bwd_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
     barrier()
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    max_ms = float(t.item())
     units_per_step = B * L * H * W            # per rank
-    value = world * units_per_step * args.steps / 1e6 / (max_ms / 1e3)
+    _, max_ms, thr = sharding.aggregate_throughput(units_per_step * args.steps, total_ms, dev)
+    value = thr / 1e6
 
-    # ---- end to end through the public API with pinned host buffers -------------------------------
-    hx = [x.cpu().pin_memory() for x in xs[:2]]
-    hth = [t_.cpu().pin_memory() for t_ in ths[:2]]
-    hgo = [g_.cpu().pin_memory() for g_ in gos[:2]]
-    h_out = torch.empty((B, 4, H, W), dtype=dtype).pin_memory()
-    h_gx = torch.empty((B, L, 4, H, W), dtype=dtype).pin_memory()
-    h_gt = torch.empty((B, L, 2, 3), dtype=torch.float32).pin_memory()
-    h2d = hx[0].numel() * es + hth[0].numel() * 4 + hgo[0].numel() * es
-    d2h = h_out.numel() * es + h_gx.numel() * es + h_gt.numel() * 4
-
-    def e2e_step(k):
-        xd = hx[k].to(dev, non_blocking=True).requires_grad_(True)
-        td = hth[k].to(dev, non_blocking=True).requires_grad_(True)
-        god = hgo[k].to(dev, non_blocking=True)
-        o = mr.render(xd, td)
-        o.backward(god)
-        h_out.copy_(o.detach(), non_blocking=True)
-        h_gx.copy_(xd.grad, non_blocking=True)
-        h_gt.copy_(td.grad, non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()      # the step's results are on the host
-
-    e2e_steps = 0 if args.kernels_only else max(3, min(args.steps, 10))
-    for i in range(2 if e2e_steps else 0):
-        e2e_step(i % 2)
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for i in range(e2e_steps):
-        e2e_step(i % 2)
-    e1.record(stream)
+    # ---- the same step on translation-only placements (what STNv2c emits), kernels only ---------------
+    ths_T = [synth.make_theta(B, L, "T", seed=1000 * rank + k, cover_back=False).to(dev) for k in range(NSETS)]
+    ths_I, ths[:] = list(ths), ths_T
+    for i in range(3):
+        fwd(i % NSETS); bwd(i % NSETS)
     torch.cuda.synchronize(dev)
-    te = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * units_per_step * e2e_steps / 1e6 / (float(te.item()) / 1e3) if e2e_steps else None
+    t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0e.record(stream)
+    for i in range(args.steps):
+        fwd(i % NSETS); bwd(i % NSETS)
+    t1e.record(stream)
+    torch.cuda.synchronize(dev)
+    _, ms_T, thr_T = sharding.aggregate_throughput(units_per_step * args.steps, t0e.elapsed_time(t1e), dev)
+    ths[:] = ths_I
+
+    # ---- end to end through the C ABI with pinned HOST buffers (H2D + kernels + D2H in the timed region) ----
+    e2e_steps = 0 if args.kernels_only else max(3, min(args.steps, 10))
+    e2e_value, h2d, d2h = None, 0, 0
+    if e2e_steps:
+        from montage_gan_b200.host import HostRenderer
+        hr = HostRenderer(B, L, H, W, dtype, chunk_B=args.chunk, device=dev)
+        hx = [x.cpu().pin_memory() for x in xs[:2]]
+        hth = [t_.cpu().pin_memory() for t_ in ths[:2]]
+        hgo = [g_.cpu().pin_memory() for g_ in gos[:2]]
+        h2d = hx[0].numel() * es + hth[0].numel() * 4 + hgo[0].numel() * es
+        d2h = hr.out.numel() * es + hr.grad_x.numel() * es + hr.grad_theta.numel() * 4
+        for i in range(2):
+            hr.fwd_bwd(hx[i % 2], hth[i % 2], hgo[i % 2])
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(e2e_steps):
+            hr.fwd_bwd(hx[i % 2], hth[i % 2], hgo[i % 2])       # synchronises: the step's results are on the host
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        _, _, thr_e = sharding.aggregate_throughput(units_per_step * e2e_steps, e0.elapsed_time(e1), dev)
+        e2e_value = thr_e / 1e6
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -286,7 +291,8 @@ def run_cuda_arm(args, wl):
         # dominant kernel = the backward pass (scatter + theta reduction)
         achieved = bb / 1e9 / (bwd_ms / 1e3)
         roofline = {"bound": "hbm", "kernel": "render backward (mgr_render_backward)", "achieved": achieved,
-                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": (measured_traffic(args.workload) or {}).get("bytes"),
+                    "traffic_source": (measured_traffic(args.workload) or {}).get("source"), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": bb,
                     "forward": {"achieved": fb / 1e9 / (fwd_ms / 1e3), "frac": fb / 1e9 / (fwd_ms / 1e3) / peak,
                                 "ms": fwd_ms, "algorithmic_bytes_per_launch": fb},
@@ -306,7 +312,12 @@ def run_cuda_arm(args, wl):
                            "sharding": f"batch-sharded, {B} samples per GPU, no data-path collective"},
                 "roofline": roofline, "cpu_baseline": cpu_base,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "steps": e2e_steps, "api": "montage_gan_b200.render.render + autograd, pinned host buffers"},
+                        "steps": e2e_steps, "api": "mgr_render_fwd_bwd_host (C ABI, pinned host buffers, "
+                                                   f"chunks of {args.chunk} samples on 3 streams)"},
+                "translation_only": {"value": thr_T / 1e6, "unit": UNIT, "ms_per_step": ms_T / args.steps,
+                                     "frac": (fb + bb) / 1e9 / (ms_T / args.steps / 1e3) / peak,
+                                     "note": "same workload with the placements STNv2c emits (pure translations, "
+                                             "U(-1,1)); kernels only, inputs resident"},
                 "gpu_launches": int(launches), "clocks": clocks.summary(),
                 "wall_s_timed_region": t_wall}
         print(json.dumps(line), flush=True)
@@ -322,6 +333,7 @@ def main():
     ap.add_argument("--impl", default="cuda", choices=["cuda", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU baseline sampling budget")
+    ap.add_argument("--chunk", type=int, default=8, help="samples per chunk of the host-buffer pipeline (e2e)")
     ap.add_argument("--kernels-only", action="store_true",
                     help="skip the e2e and cpu_baseline legs (for ncu captures; not a valid bench line)")
     args = ap.parse_args()

@@ -210,4 +210,97 @@ int mgr_pad_stack_layer(const void* src, const int64_t* src_strides, void* dst, 
   }
 }
 
+
+// ---- end-to-end entry point with HOST buffers: chunked, double-buffered, three streams ----------------
+namespace {
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+struct HostSlot { char *x, *theta, *go, *out, *sav, *gx, *gt, *ws; };
+size_t host_slot_bytes(int cb, int L, int H, int W, int dtype, HostSlot* s, char* base) {
+  const size_t es = dtype == MGR_F32 ? 4 : 2;
+  const size_t nx = (size_t)cb * L * 4 * H * W * es, no = (size_t)cb * 4 * H * W * es, nt = (size_t)cb * L * 6 * 4;
+  const size_t nsav = mgr_saved_alpha_bytes(cb, L, H, W, dtype);
+  const size_t nws = mgr_render_backward_workspace_bytes(cb, L, H, W, dtype, 1, 3);
+  size_t off = 0;
+  auto take = [&](char** p, size_t n) { if (s) *p = base + off; off += align256(n); };
+  take(s ? &s->x : nullptr, nx); take(s ? &s->theta : nullptr, nt); take(s ? &s->go : nullptr, no);
+  take(s ? &s->out : nullptr, no); take(s ? &s->sav : nullptr, nsav); take(s ? &s->gx : nullptr, nx);
+  take(s ? &s->gt : nullptr, nt); take(s ? &s->ws : nullptr, nws);
+  return off;
+}
+}  // namespace
+
+size_t mgr_render_host_workspace_bytes(int chunk_B, int L, int H, int W, int dtype) {
+  if (chunk_B <= 0 || L <= 0 || H <= 0 || W <= 0) return 0;
+  return 2 * host_slot_bytes(chunk_B, L, H, W, dtype, nullptr, nullptr);
+}
+
+int mgr_render_fwd_bwd_host(const void* h_x, const float* h_theta, const void* h_grad_out, void* h_out,
+                            void* h_grad_x, float* h_grad_theta, void* d_workspace, size_t d_workspace_bytes,
+                            int chunk_B, int B, int L, int H, int W, int dtype, int range_mode, void* stream) {
+  if (!h_x || !h_theta || !h_grad_out || !h_out || !h_grad_x || !h_grad_theta)
+    return fail(MGR_ERR_INVALID_ARGUMENT, "a host buffer is NULL");
+  if (chunk_B < 1 || B < 0 || L < 1 || H < 1 || W < 1) return fail(MGR_ERR_INVALID_ARGUMENT, "bad shape");
+  if (dtype != MGR_F32 && dtype != MGR_BF16 && dtype != MGR_F16) return fail(MGR_ERR_INVALID_ARGUMENT, "bad dtype %d", dtype);
+  if (B == 0) return MGR_OK;
+  const size_t need = mgr_render_host_workspace_bytes(chunk_B, L, H, W, dtype);
+  if (!d_workspace || d_workspace_bytes < need)
+    return fail(MGR_ERR_WORKSPACE_TOO_SMALL, "device workspace %zu bytes < required %zu", d_workspace_bytes, need);
+  HostSlot slot[2];
+  const size_t per = host_slot_bytes(chunk_B, L, H, W, dtype, &slot[0], (char*)d_workspace);
+  host_slot_bytes(chunk_B, L, H, W, dtype, &slot[1], (char*)d_workspace + per);
+  const size_t es = dtype == MGR_F32 ? 4 : 2;
+  const size_t sx = (size_t)L * 4 * H * W * es, so = (size_t)4 * H * W * es, st_ = (size_t)L * 6 * 4;   // bytes per sample
+  cudaStream_t user = (cudaStream_t)stream, s_in, s_out;
+  MGR_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+  MGR_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+  cudaEvent_t start, h2d[2], comp[2], freed[2];
+  MGR_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+  for (int k = 0; k < 2; ++k) {
+    MGR_CUDA(cudaEventCreateWithFlags(&h2d[k], cudaEventDisableTiming));
+    MGR_CUDA(cudaEventCreateWithFlags(&comp[k], cudaEventDisableTiming));
+    MGR_CUDA(cudaEventCreateWithFlags(&freed[k], cudaEventDisableTiming));
+  }
+  // the copy streams start after whatever the caller has queued on `user`
+  MGR_CUDA(cudaEventRecord(start, user));
+  MGR_CUDA(cudaStreamWaitEvent(s_in, start, 0));
+  MGR_CUDA(cudaStreamWaitEvent(s_out, start, 0));
+  int rc = MGR_OK;
+  const int nchunks = (B + chunk_B - 1) / chunk_B;
+  for (int c = 0; c < nchunks && rc == MGR_OK; ++c) {
+    const int k = c & 1, b0 = c * chunk_B, cb = (B - b0 < chunk_B) ? B - b0 : chunk_B;
+    const HostSlot& S = slot[k];
+    if (c >= 2) MGR_CUDA(cudaStreamWaitEvent(s_in, freed[k], 0));          // slot drained by the D2H of chunk c-2
+    MGR_CUDA(cudaMemcpyAsync(S.x, (const char*)h_x + b0 * sx, cb * sx, cudaMemcpyHostToDevice, s_in));
+    MGR_CUDA(cudaMemcpyAsync(S.theta, (const char*)h_theta + b0 * st_, cb * st_, cudaMemcpyHostToDevice, s_in));
+    MGR_CUDA(cudaMemcpyAsync(S.go, (const char*)h_grad_out + b0 * so, cb * so, cudaMemcpyHostToDevice, s_in));
+    MGR_CUDA(cudaEventRecord(h2d[k], s_in));
+    MGR_CUDA(cudaStreamWaitEvent(user, h2d[k], 0));
+    rc = mgr_render_forward(S.x, nullptr, (const float*)S.theta, S.out, S.sav, cb, L, H, W, dtype, range_mode, user);
+    if (rc == MGR_OK)
+      rc = mgr_render_backward(S.x, nullptr, (const float*)S.theta, S.out, S.go, S.sav, S.gx, (float*)S.gt, S.ws,
+                               mgr_render_backward_workspace_bytes(cb, L, H, W, dtype, 1, 3), cb, L, H, W, dtype,
+                               range_mode, 3, user);
+    if (rc != MGR_OK) break;
+    MGR_CUDA(cudaEventRecord(comp[k], user));
+    MGR_CUDA(cudaStreamWaitEvent(s_out, comp[k], 0));
+    MGR_CUDA(cudaMemcpyAsync((char*)h_out + b0 * so, S.out, cb * so, cudaMemcpyDeviceToHost, s_out));
+    MGR_CUDA(cudaMemcpyAsync((char*)h_grad_x + b0 * sx, S.gx, cb * sx, cudaMemcpyDeviceToHost, s_out));
+    MGR_CUDA(cudaMemcpyAsync((char*)h_grad_theta + b0 * st_, S.gt, cb * st_, cudaMemcpyDeviceToHost, s_out));
+    MGR_CUDA(cudaEventRecord(freed[k], s_out));
+  }
+  // `user` completes only when the last results have landed on the host
+  if (rc == MGR_OK) {
+    cudaEvent_t done;
+    MGR_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+    MGR_CUDA(cudaEventRecord(done, s_out));
+    MGR_CUDA(cudaStreamWaitEvent(user, done, 0));
+    cudaEventDestroy(done);
+  }
+  cudaEventDestroy(start);
+  for (int k = 0; k < 2; ++k) { cudaEventDestroy(h2d[k]); cudaEventDestroy(comp[k]); cudaEventDestroy(freed[k]); }
+  cudaStreamDestroy(s_in);        // destruction is deferred by the runtime until the queued work has drained
+  cudaStreamDestroy(s_out);
+  return rc;
+}
+
 }  // extern "C"

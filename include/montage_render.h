@@ -150,6 +150,22 @@ int mgr_translation_to_theta(const float* translation, float* theta, long long n
 int mgr_pad_stack_layer(const void* src, const int64_t* src_strides, void* dst, int B, int L, int l,
                         int h, int w, int H, int W, float pad_value, int dtype, void* stream);
 
+/*
+ * End to end with HOST buffers: out, grad_x, grad_theta = fwd+bwd(x, theta, grad_out), everything in
+ * (preferably pinned) host memory, laid out exactly like the device tensors.  The batch is cut
+ * into chunks of chunk_B samples that flow through two device slots on three streams (H2D copy,
+ * kernels on `stream`, D2H copy) so PCIe traffic in both directions overlaps the kernels.  The
+ * call is asynchronous: `stream` completes when the last result byte has reached the host.
+ * d_workspace: device scratch of mgr_render_host_workspace_bytes(chunk_B, ...) bytes.
+ *   This is the call bench.py times for its "e2e" figure; in the reference the same data path is
+ *   .to(device) + the chain of custom/loss_aio.py:238-257 + .cpu().
+ */
+size_t mgr_render_host_workspace_bytes(int chunk_B, int L, int H, int W, int dtype);
+int mgr_render_fwd_bwd_host(const void* h_x, const float* h_theta, const void* h_grad_out, void* h_out,
+                            void* h_grad_x, float* h_grad_theta, void* d_workspace,
+                            size_t d_workspace_bytes, int chunk_B, int B, int L, int H, int W,
+                            int dtype, int range_mode, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

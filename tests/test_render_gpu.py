@@ -366,3 +366,19 @@ def test_modules_drop_in():
     w2, t2 = stn(x)
     ren(w2).square().mean().backward()
     assert stn.fc_loc[2].bias.grad.abs().sum().item() > 0
+
+
+def test_host_buffer_pipeline_matches_device_path():
+    from montage_gan_b200.host import HostRenderer
+    B, L, H, W = 11, 4, 32, 32                      # 11 samples in chunks of 4: ragged last chunk
+    x = synth.make_layers(B, L, H, W, "S", seed=2).pin_memory()
+    th = synth.make_theta(B, L, "I", seed=2).pin_memory()
+    go = synth.make_grad_out(B, H, W, seed=2).pin_memory()
+    hr = HostRenderer(B, L, H, W, torch.float32, chunk_B=4)
+    out, gx, gt = hr.fwd_bwd(x, th, go)
+    ref = _run_cuda(x, th, go)
+    assert np.array_equal(out.numpy(), ref["out"])
+    assert rel_err(gx.numpy(), ref["grad_x"]) < 1e-6
+    assert rel_err(gt.numpy(), ref["grad_theta"]) < 1e-5
+    with pytest.raises(ValueError):
+        hr.fwd_bwd(x.cuda(), th, go)
