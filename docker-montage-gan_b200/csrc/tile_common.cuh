@@ -48,12 +48,13 @@ __device__ __forceinline__ LayerPlan plan_layer(const float* __restrict__ th, in
   LayerPlan p;
   p.aff = make_tile_affine(th, H, W, j0 + kTW / 2, i0 + kTH / 2);
   const TileAffine& t = p.aff;
-  const float lo_ = -(float)(kTW / 2), hi_ = (float)(kTW / 2 - 1);   // dj, di in [-16, 15]
+  const float lo_ = -(float)(kTW / 2), hi_ = (float)(kTW / 2 - 1);   // dj in [-kTW/2, kTW/2 - 1]
+  const float lov = -(float)(kTH / 2), hiv = (float)(kTH / 2 - 1);   // di in [-kTH/2, kTH/2 - 1]
   const float eps = 2e-3f;   // fp32 rounding of per-pixel coordinates is ~1e-5 px; stay well clear
-  const float xmin = t.rx + fminf(t.a00 * lo_, t.a00 * hi_) + fminf(t.a01 * lo_, t.a01 * hi_) - eps;
-  const float xmax = t.rx + fmaxf(t.a00 * lo_, t.a00 * hi_) + fmaxf(t.a01 * lo_, t.a01 * hi_) + eps;
-  const float ymin = t.ry + fminf(t.a10 * lo_, t.a10 * hi_) + fminf(t.a11 * lo_, t.a11 * hi_) - eps;
-  const float ymax = t.ry + fmaxf(t.a10 * lo_, t.a10 * hi_) + fmaxf(t.a11 * lo_, t.a11 * hi_) + eps;
+  const float xmin = t.rx + fminf(t.a00 * lo_, t.a00 * hi_) + fminf(t.a01 * lov, t.a01 * hiv) - eps;
+  const float xmax = t.rx + fmaxf(t.a00 * lo_, t.a00 * hi_) + fmaxf(t.a01 * lov, t.a01 * hiv) + eps;
+  const float ymin = t.ry + fminf(t.a10 * lo_, t.a10 * hi_) + fminf(t.a11 * lov, t.a11 * hiv) - eps;
+  const float ymax = t.ry + fmaxf(t.a10 * lo_, t.a10 * hi_) + fmaxf(t.a11 * lov, t.a11 * hiv) + eps;
   p.x_lo = p.y_lo = p.bw = p.bh = 0;
   p.lrx = p.lry = 0.f;
   p.pad_ = 0;
