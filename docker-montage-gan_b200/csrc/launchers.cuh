@@ -3,6 +3,7 @@
 #include "mgr_errors.h"
 #include "render_direct.cuh"
 #include "render_bwd_tiled.cuh"
+#include "render_shift.cuh"
 #include "render_tiled.cuh"
 #include "warp_ops.cuh"
 
@@ -33,8 +34,16 @@ int launch_forward(const void* x, const float* theta, void* out, void* sav, cons
     }
     dim3 grid((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B);
     using SA = typename SavedAlpha<T>::type;
-    if (sav) render_fwd_tiled<T, true><<<grid, kTiledThreads, smem, s>>>((const T*)x, theta, (T*)out, (SA*)sav, g);
-    else render_fwd_tiled<T, false><<<grid, kTiledThreads, smem, s>>>((const T*)x, theta, (T*)out, nullptr, g);
+    const int shift = debug_path() != 2;        // all-translation samples go to the stencil kernel
+    if (sav) render_fwd_tiled<T, true><<<grid, kTiledThreads, smem, s>>>((const T*)x, theta, (T*)out, (SA*)sav, g, shift);
+    else render_fwd_tiled<T, false><<<grid, kTiledThreads, smem, s>>>((const T*)x, theta, (T*)out, nullptr, g, shift);
+    if (shift) {
+      MGR_CUDA(cudaGetLastError());
+      count_launch();
+      const size_t smem2 = shift_fwd_smem_bytes(g.L, sizeof(Vec));
+      if (sav) render_fwd_shift<T, true><<<grid, kTiledThreads, smem2, s>>>((const T*)x, theta, (T*)out, (SA*)sav, g);
+      else render_fwd_shift<T, false><<<grid, kTiledThreads, smem2, s>>>((const T*)x, theta, (T*)out, nullptr, g);
+    }
     MGR_CUDA(cudaGetLastError());
     count_launch();
     return MGR_OK;
@@ -97,12 +106,13 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
     const size_t smem = tiled_smem_bytes(g.L, sizeof(Vec)) + sizeof(float) * 6 * g.L +
                         sizeof(float) * (size_t)g.L * kPx * kTiledThreads;          // + transmittance stash
     dim3 grid((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B);
+    const int shift = debug_path() != 2;
     if (nt)
       render_bwd_pass1<T, true><<<grid, kTiledThreads, smem, s>>>((const T*)x, theta, (const T*)out, (const T*)gout,
-                                                                  (const SA*)sav, rec, gp, gtheta, g);
+                                                                  (const SA*)sav, rec, gp, gtheta, g, shift);
     else
       render_bwd_pass1<T, false><<<grid, kTiledThreads, smem, s>>>((const T*)x, theta, (const T*)out, (const T*)gout,
-                                                                   (const SA*)sav, rec, gp, nullptr, g);
+                                                                   (const SA*)sav, rec, gp, nullptr, g, shift);
     MGR_CUDA(cudaGetLastError());
     count_launch();
     if (nx) {
@@ -110,7 +120,29 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
       inverse_plans_kernel<<<(g.B * g.L + 127) / 128, 128, 0, s>>>(theta, inv, g.B * g.L, g.H, g.W);
       MGR_CUDA(cudaGetLastError());
       count_launch();
-      render_bwd_pass2<T><<<grid2, kP2W * kP2H, 0, s>>>(inv, rec, gp, (T*)gx, g);
+      render_bwd_pass2<T><<<grid2, kP2W * kP2H, 0, s>>>(inv, rec, gp, (T*)gx, g, shift);
+      MGR_CUDA(cudaGetLastError());
+      count_launch();
+    }
+    if (shift) {
+      static bool configured2 = false;
+      if (!configured2) {
+        MGR_CUDA(cudaFuncSetAttribute(render_bwd_shift<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MGR_CUDA(cudaFuncSetAttribute(render_bwd_shift<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MGR_CUDA(cudaFuncSetAttribute(render_bwd_shift<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured2 = true;
+      }
+      const size_t smem3 = shift_bwd_smem_bytes(g.L, sizeof(Vec));
+      dim3 grid3((g.W + 1 + kAnchor - 1) / kAnchor, (g.H + 1 + kAnchor - 1) / kAnchor, g.B);
+      if (nx && nt)
+        render_bwd_shift<T, true, true><<<grid3, kTiledThreads, smem3, s>>>((const T*)x, theta, (const T*)out, (const T*)gout,
+                                                                            (const SA*)sav, (T*)gx, gtheta, g);
+      else if (nx)
+        render_bwd_shift<T, true, false><<<grid3, kTiledThreads, smem3, s>>>((const T*)x, theta, (const T*)out, (const T*)gout,
+                                                                             (const SA*)sav, (T*)gx, nullptr, g);
+      else
+        render_bwd_shift<T, false, true><<<grid3, kTiledThreads, smem3, s>>>((const T*)x, theta, (const T*)out, (const T*)gout,
+                                                                             (const SA*)sav, nullptr, gtheta, g);
       MGR_CUDA(cudaGetLastError());
       count_launch();
     }

@@ -90,6 +90,19 @@ __device__ __forceinline__ Taps make_taps(const TileAffine& t, int dj, int di, i
   return p;
 }
 
+// A placement that is exactly [[1,0,dx],[0,1,dy]] with a sane shift: what convert_translate_to_2x3 builds
+// (custom_utils/image_utils.py:316-335).  The shift kernels and the general kernels partition the batch on it.
+__device__ __forceinline__ bool is_pure_shift(const float* __restrict__ th) {
+  return th[0] == 1.f && th[1] == 0.f && th[3] == 0.f && th[4] == 1.f && fabsf(th[2]) < 1.0e6f && fabsf(th[5]) < 1.0e6f;
+}
+
+// true iff every layer of a sample is a pure translation (uniform over the CTA; contains a barrier)
+__device__ __forceinline__ bool cta_all_shift(const float* __restrict__ theta_b, int L, int tid, int nthreads) {
+  bool ok = true;
+  for (int l = tid; l < L; l += nthreads) ok = ok && is_pure_shift(theta_b + 6 * l);
+  return __syncthreads_and(ok);
+}
+
 // normalised output coordinate of pixel index k along an axis of size n: (2k+1)/n - 1
 __device__ __forceinline__ float norm_coord(int k, int n) { return (float)(2 * k + 1) / (float)n - 1.f; }
 

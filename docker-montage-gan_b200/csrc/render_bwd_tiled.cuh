@@ -33,7 +33,8 @@ template <typename T, bool kNeedTheta>
 __global__ void __launch_bounds__(kTiledThreads, 2)
 render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const T* __restrict__ out,
                  const T* __restrict__ gout, const typename SavedAlpha<T>::type* __restrict__ sav,
-                 float2* __restrict__ rec, float4* __restrict__ gp, float* __restrict__ gtheta, Geometry g) {
+                 float2* __restrict__ rec, float4* __restrict__ gp, float* __restrict__ gtheta, Geometry g,
+                 int skip_shift) {
   using Vec = typename Texel<T>::Vec;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Vec* buf = reinterpret_cast<Vec*>(smem_raw);                                            // [kCapTexels]
@@ -42,6 +43,7 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
   const int tid = threadIdx.x;
   float* Tst = gth_acc + 6 * g.L + tid;                     // [L][kPx][256]: transmittance in front of layer l
   const int b = blockIdx.z;
+  if (skip_shift && cta_all_shift(theta + (long long)b * g.L * 6, g.L, tid, kTiledThreads)) return;   // render_bwd_shift's
   const int j0 = blockIdx.x * kTW, i0 = blockIdx.y * kTH;
   const int tx = tid & 31, ty = tid >> 5;
   for (int l = tid; l < g.L; l += kTiledThreads)
@@ -244,8 +246,7 @@ static __global__ void inverse_plans_kernel(const float* __restrict__ theta, Inv
   q.r10 = fabs(a10) > 1e-6 ? (float)(1.0 / a10) : 0.f;
   q.wide = (2.0 * rj > 3.5) || (2.0 * ri > 3.5);
   // what STNv2c emits (convert_translate_to_2x3, image_utils.py:316-335): the adjoint is a fixed 2x2 stencil
-  q.shift_only = (th[0] == 1.f && th[1] == 0.f && th[3] == 0.f && th[4] == 1.f && isfinite(q.c0) && isfinite(q.c1) &&
-                  fabs(q.c0) < 1.0e8 && fabs(q.c1) < 1.0e8);
+  q.shift_only = is_pure_shift(th);
   const double fX = floor(q.c0), fY = floor(q.c1);
   q.X = q.shift_only ? (int)fX : 0; q.Y = q.shift_only ? (int)fY : 0;
   q.fx = q.shift_only ? (float)(q.c0 - fX) : 0.f; q.fy = q.shift_only ? (float)(q.c1 - fY) : 0.f;
@@ -257,7 +258,7 @@ constexpr int kP2W = 32, kP2H = 8;
 template <typename T>
 __global__ void __launch_bounds__(kP2W * kP2H)
 render_bwd_pass2(const InverseLayer* __restrict__ plans, const float2* __restrict__ rec, const float4* __restrict__ gp,
-                 T* __restrict__ gx, Geometry g) {
+                 T* __restrict__ gx, Geometry g, int skip_shift) {
   __shared__ float s_jcf, s_icf;
   __shared__ int s_JC, s_IC, s_ok;
   const int n = blockIdx.z;                     // b * L + l
@@ -265,6 +266,11 @@ render_bwd_pass2(const InverseLayer* __restrict__ plans, const float2* __restric
   const int x0b = blockIdx.x * kP2W, y0b = blockIdx.y * kP2H;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const InverseLayer& L_ = plans[n];
+  if (skip_shift) {           // all-translation samples are written by render_bwd_shift
+    bool all = true;
+    for (int l = 0; l < g.L; ++l) all = all && plans[b * g.L + l].shift_only;
+    if (all) return;
+  }
   if (L_.shift_only) {
     // pure translation: texel (x, y) is tap (x0 + dx, y0 + dy) of pixel (x - X - dx, y - Y - dy), dx, dy in {0, 1},
     // with weights (dx ? fx : 1 - fx) (dy ? fy : 1 - fy) -- a fixed 2x2 stencil, uniform over the layer

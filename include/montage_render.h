@@ -70,7 +70,8 @@ const char* mgr_last_error(void);
  * bench.py differences it around the timed region to report "gpu_launches". */
 long long mgr_kernel_launch_count(void);
 /* Testing / A-B timing only: 0 = automatic kernel selection (default), 1 = force the general
- * direct-gather kernels even where the tiled shared-memory kernels apply.  Process-wide. */
+ * direct-gather kernels even where the tiled shared-memory kernels apply, 2 = tiled kernels but
+ * without the pure-translation stencil kernels.  Process-wide. */
 int mgr_set_debug_path(int path);
 
 /*

@@ -47,7 +47,9 @@ def main():
         for tf in args.thetas.split(","):
             xs = [synth.make_layers(gen_B, L, H, W, args.layers, seed=k).repeat(reps, 1, 1, 1, 1)[:B].to(dev, dtype).contiguous()
                   for k in range(nsets)]
-            ths = [synth.make_theta(B, L, tf, seed=k).to(dev) for k in range(nsets)]
+            # 'P' = pure translations for every layer (what STNv2c emits); 'T' keeps the covering back layer
+            ths = [(synth.make_theta(B, L, 'T', seed=k, cover_back=False) if tf == 'P' else synth.make_theta(B, L, tf, seed=k)).to(dev)
+                   for k in range(nsets)]
             gos = [synth.make_grad_out(B, H, W, seed=k).to(dev, dtype) for k in range(nsets)]
             out = torch.empty(B, 4, H, W, dtype=dtype, device=dev)
             gx = torch.empty(B, L, 4, H, W, dtype=dtype, device=dev)
