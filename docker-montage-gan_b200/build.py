@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
-]
+] + (["-DMGR_EXPERIMENT_NO_STAGE_LOADS"] if os.environ.get("MGR_EXPERIMENT_NO_STAGE_LOADS") else [])
 
 
 def _nvcc():

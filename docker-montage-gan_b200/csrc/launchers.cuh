@@ -118,9 +118,10 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
     if (nx) {
       dim3 grid2((g.W + kP2W - 1) / kP2W, (g.H + kP2H - 1) / kP2H, g.B * g.L);
       inverse_plans_kernel<<<(g.B * g.L + 127) / 128, 128, 0, s>>>(theta, inv, g.B * g.L, g.H, g.W);
+      sample_flags_kernel<<<(g.B + 127) / 128, 128, 0, s>>>(inv, g.B, g.L);
       MGR_CUDA(cudaGetLastError());
-      count_launch();
-      render_bwd_pass2<T><<<grid2, kP2W * kP2H, 0, s>>>(inv, rec, gp, (T*)gx, g, shift);
+      count_launch(2);
+      render_bwd_pass2<T><<<grid2, 256, 0, s>>>(inv, rec, gp, (T*)gx, g, shift);
       MGR_CUDA(cudaGetLastError());
       count_launch();
     }

@@ -223,6 +223,7 @@ struct InverseLayer {
   int shift_only;               // 1: pure translation (a00 = a11 = 1, a01 = a10 = 0 exactly): 2x2 stencil adjoint
   int X, Y;                     // shift_only: ix = j + X + fx, iy = i + Y + fy
   float fx, fy;
+  int all_shift;                // every layer of this sample is a pure translation (set by sample_flags_kernel)
 };
 
 static_assert(sizeof(InverseLayer) <= 128, "workspace reserves 128 B per layer plan");
@@ -253,10 +254,41 @@ static __global__ void inverse_plans_kernel(const float* __restrict__ theta, Inv
   plans[k] = q;
 }
 
-constexpr int kP2W = 32, kP2H = 8;
+// one thread per sample: are all of its layers pure translations?  (those samples belong to render_bwd_shift)
+static __global__ void sample_flags_kernel(InverseLayer* __restrict__ plans, int B, int L) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int all = 1;
+  for (int l = 0; l < L; ++l) all &= plans[b * L + l].shift_only;
+  for (int l = 0; l < L; ++l) plans[b * L + l].all_shift = all;
+}
+
+// Block of 256 threads = 32 x 8 threads, each owning a 2 x 2 block of texels -> 64 x 16 texels per CTA.
+// A 2 x 2 block shares its candidate pixels (the union of four windows is barely larger than one), the
+// record loads and the per-candidate coordinate arithmetic; the accumulators are packed fp32x2 pairs.
+constexpr int kP2W = 64, kP2H = 16;
+
+template <typename T> struct Pack2;      // two horizontally adjacent texels of one channel -> one store
+template <> struct Pack2<float> {
+  __device__ static __forceinline__ void store(float* p, float a, float b, bool two) {
+    if (two) *reinterpret_cast<float2*>(p) = make_float2(a, b); else *p = a;
+  }
+};
+template <> struct Pack2<__nv_bfloat16> {
+  __device__ static __forceinline__ void store(__nv_bfloat16* p, float a, float b, bool two) {
+    if (two) *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); else *p = __float2bfloat16_rn(a);
+  }
+};
+template <> struct Pack2<__half> {
+  __device__ static __forceinline__ void store(__half* p, float a, float b, bool two) {
+    if (two) *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b); else *p = __float2half_rn(a);
+  }
+};
+
+__device__ __forceinline__ float hat(float u) { return fmaxf(1.f - fabsf(u), 0.f); }
 
 template <typename T>
-__global__ void __launch_bounds__(kP2W * kP2H)
+__global__ void __launch_bounds__(256)
 render_bwd_pass2(const InverseLayer* __restrict__ plans, const float2* __restrict__ rec, const float4* __restrict__ gp,
                  T* __restrict__ gx, Geometry g, int skip_shift) {
   __shared__ float s_jcf, s_icf;
@@ -266,129 +298,134 @@ render_bwd_pass2(const InverseLayer* __restrict__ plans, const float2* __restric
   const int x0b = blockIdx.x * kP2W, y0b = blockIdx.y * kP2H;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const InverseLayer& L_ = plans[n];
-  if (skip_shift) {           // all-translation samples are written by render_bwd_shift
-    bool all = true;
-    for (int l = 0; l < g.L; ++l) all = all && plans[b * g.L + l].shift_only;
-    if (all) return;
-  }
+  if (skip_shift && L_.all_shift) return;      // all-translation samples are written by render_bwd_shift
+  const int hw = g.H * g.W;
+  const int x = x0b + 2 * tx, y = y0b + 2 * ty;                // top-left texel of this thread's 2 x 2 block
+  const float zs = g.m11 ? 0.5f : 1.f;          // d z / d x_texel = zs * weight
+  T* gxp = gx + (long long)n * 4 * hw + y * g.W + x;
+  const bool two = x + 1 < g.W;                 // W is even on this path (tiled_ok), kept for safety
+  f32x2 acc[2][2][2];                           // [row][col][rg | ba]
+#pragma unroll
+  for (int q = 0; q < 8; ++q) (&acc[0][0][0])[q] = 0ull;
+
   if (L_.shift_only) {
-    // pure translation: texel (x, y) is tap (x0 + dx, y0 + dy) of pixel (x - X - dx, y - Y - dy), dx, dy in {0, 1},
-    // with weights (dx ? fx : 1 - fx) (dy ? fy : 1 - fy) -- a fixed 2x2 stencil, uniform over the layer
-    const int x = x0b + tx, y = y0b + ty;
+    // pure translation: texel (x, y) is tap (dx, dy) of pixel (x - X - dx, y - Y - dy) with the layer-wide
+    // weights (dx ? fx : 1 - fx)(dy ? fy : 1 - fy): a fixed 2 x 2 stencil; the 2 x 2 block reads 3 x 3 records
     if (x >= g.W || y >= g.H) return;
-    const int hw = g.H * g.W;
-    const int j1 = x - L_.X, i1 = y - L_.Y;                   // the pixel for which this texel is tap (0, 0)
-    const float wx0 = 1.f - L_.fx, wx1 = L_.fx, wy0 = 1.f - L_.fy, wy1 = L_.fy;
+    const float wx[2] = {1.f - L_.fx, L_.fx}, wy[2] = {1.f - L_.fy, L_.fy};
     const float2* recn = rec + (long long)n * hw;
     const float4* gpb = gp + (long long)b * hw;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
 #pragma unroll
-    for (int dy = 0; dy < 2; ++dy) {
-      const int i = i1 - dy;
+    for (int di = -1; di <= 1; ++di) {
+      const int i = y - L_.Y + di;
       if ((unsigned)i >= (unsigned)g.H) continue;
-      const float wy = dy ? wy1 : wy0;
 #pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const int j = j1 - dx;
+      for (int dj = -1; dj <= 1; ++dj) {
+        const int j = x - L_.X + dj;
         if ((unsigned)j >= (unsigned)g.W) continue;
-        const float wgt = wy * (dx ? wx1 : wx0);
         const float2 r = __ldg(recn + i * g.W + j);
         const float4 G = __ldg(gpb + i * g.W + j);
-        const float wt = wgt * r.x;
-        acc0 = fmaf(wt, G.x, acc0);
-        acc1 = fmaf(wt, G.y, acc1);
-        acc2 = fmaf(wt, G.z, acc2);
-        acc3 = fmaf(wgt, r.y, acc3);
+        const f32x2 grg = pk(G.x * r.x, G.y * r.x), gba = pk(G.z * r.x, r.y);
+#pragma unroll
+        for (int ky = 0; ky < 2; ++ky) {
+          const int ty_ = ky - di;              // tap row index of texel row ky for this pixel: (y + ky) - (i + Y)
+          if (ty_ < 0 || ty_ > 1) continue;
+#pragma unroll
+          for (int kx = 0; kx < 2; ++kx) {
+            const int tx_ = kx - dj;
+            if (tx_ < 0 || tx_ > 1) continue;
+            const f32x2 w2 = bc(wy[ty_] * wx[tx_]);
+            acc[ky][kx][0] = fma2(w2, grg, acc[ky][kx][0]);
+            acc[ky][kx][1] = fma2(w2, gba, acc[ky][kx][1]);
+          }
+        }
       }
     }
-    const float zs = g.m11 ? 0.5f : 1.f;
-    T* gxp = gx + (long long)n * 4 * hw + y * g.W + x;
-    st(gxp, zs * acc0);
-    st(gxp + hw, zs * acc1);
-    st(gxp + 2 * hw, zs * acc2);
-    st(gxp + 3 * hw, zs * acc3);
-    return;
-  }
-  if (threadIdx.x == 0) {
-    // pre-image of the block centre, split into integer + fraction in double precision
-    const double xc = x0b + 0.5 * kP2W - L_.c0, yc = y0b + 0.5 * kP2H - L_.c1;
-    const double jc = L_.i00 * xc + L_.i01 * yc, ic = L_.i10 * xc + L_.i11 * yc;
-    int ok = L_.valid && isfinite(jc) && isfinite(ic) && fabs(jc) < 1.0e8 && fabs(ic) < 1.0e8;
-    const double fj = floor(jc), fi = floor(ic);
-    s_JC = ok ? (int)fj : 0; s_IC = ok ? (int)fi : 0;
-    s_jcf = ok ? (float)(jc - fj) : 0.f; s_icf = ok ? (float)(ic - fi) : 0.f;
-    s_ok = ok;
-  }
-  const float a00 = L_.a00, a01 = L_.a01, a10 = L_.a10, a11 = L_.a11;
-  const float i00 = (float)L_.i00, i01 = (float)L_.i01, i10 = (float)L_.i10, i11 = (float)L_.i11;
-  const float rj = L_.rj, ri = L_.ri;
-  const int wide = L_.wide;
-  __syncthreads();
-  const int x = x0b + tx, y = y0b + ty;
-  if (x >= g.W || y >= g.H) return;
-  const int hw = g.H * g.W;
-  T* gxp = gx + (long long)n * 4 * hw + y * g.W + x;
-  float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-  if (s_ok) {
-    const int JC = s_JC, IC = s_IC;
-    const float jcf = s_jcf, icf = s_icf;
-    const float dxl = (float)tx - 0.5f * kP2W, dyl = (float)ty - 0.5f * kP2H;   // texel - block centre
-    // pre-image of this texel relative to (JC, IC); candidates are the integer points within (rj, ri) of it,
-    // clamped to the output image (in float first: the window of a near-singular placement is huge)
-    const float pj = jcf + i00 * dxl + i01 * dyl;
-    const float pi = icf + i10 * dxl + i11 * dyl;
-    const float mlo = fmaxf(ceilf(pj - rj), (float)(-JC)), mhi = fminf(floorf(pj + rj), (float)(g.W - 1 - JC));
-    const float nlo = fmaxf(ceilf(pi - ri), (float)(-IC)), nhi = fminf(floorf(pi + ri), (float)(g.H - 1 - IC));
-    if (mlo <= mhi && nlo <= nhi) {
-      const int m0 = (int)mlo, m1 = (int)mhi, n0 = (int)nlo, n1 = (int)nhi;
-      float di = nlo - icf;
-      const float2* recn = rec + (long long)n * hw + ((IC + n0) * g.W + JC);
-      const float4* gpb = gp + (long long)b * hw + ((IC + n0) * g.W + JC);
-      const float dj0 = mlo - jcf;
-      for (int nn = n0; nn <= n1; ++nn, di += 1.f, recn += g.W, gpb += g.W) {
-        const float ub = fmaf(a01, di, -dxl), vb = fmaf(a11, di, -dyl);
-        int ma = m0, mb = m1;
-        float dja = dj0;
-        if (wide) {
-          // magnifying or near-singular placement: the bounding box of a skinny pre-image parallelogram is
-          // mostly empty.  Solve |a00 dj + ub| < 1 and |a10 dj + vb| < 1 for this row (dj = mm - jcf) and
-          // keep one candidate of slack on either side (its weight is 0 anyway).
-          float lo = -3.0e9f, hi = 3.0e9f;
-          if (L_.r00 != 0.f) {
-            const float t0 = (-1.f - ub) * L_.r00, t1 = (1.f - ub) * L_.r00;
-            lo = fmaxf(lo, fminf(t0, t1)); hi = fminf(hi, fmaxf(t0, t1));
-          } else if (fabsf(ub) >= 1.f) { hi = -3.0e9f; }
-          if (L_.r10 != 0.f) {
-            const float t0 = (-1.f - vb) * L_.r10, t1 = (1.f - vb) * L_.r10;
-            lo = fmaxf(lo, fminf(t0, t1)); hi = fminf(hi, fmaxf(t0, t1));
-          } else if (fabsf(vb) >= 1.f) { hi = -3.0e9f; }
-          lo = fmaxf(floorf(lo + jcf) - 1.f, mlo);
-          hi = fminf(ceilf(hi + jcf) + 1.f, mhi);
-          if (!(lo <= hi)) continue;
-          ma = (int)lo; mb = (int)hi;
-          dja = lo - jcf;
-        }
-        float u = fmaf(a00, dja, ub);                                  // (ix, iy)(candidate) - (x, y)
-        float v = fmaf(a10, dja, vb);
+  } else {
+    if (threadIdx.x == 0) {
+      // pre-image of the CTA's centre, split into integer + fraction in double precision
+      const double xc = x0b + 0.5 * kP2W - L_.c0, yc = y0b + 0.5 * kP2H - L_.c1;
+      const double jc = L_.i00 * xc + L_.i01 * yc, ic = L_.i10 * xc + L_.i11 * yc;
+      const int ok = L_.valid && isfinite(jc) && isfinite(ic) && fabs(jc) < 1.0e8 && fabs(ic) < 1.0e8;
+      const double fj = floor(jc), fi = floor(ic);
+      s_JC = ok ? (int)fj : 0; s_IC = ok ? (int)fi : 0;
+      s_jcf = ok ? (float)(jc - fj) : 0.f; s_icf = ok ? (float)(ic - fi) : 0.f;
+      s_ok = ok;
+    }
+    const float a00 = L_.a00, a01 = L_.a01, a10 = L_.a10, a11 = L_.a11;
+    const float i00 = (float)L_.i00, i01 = (float)L_.i01, i10 = (float)L_.i10, i11 = (float)L_.i11;
+    // half extents of the pre-image of the 2 x 2 block's support: a texel's (-1,1)^2 grown by +-0.5
+    const float rj = L_.rj + 0.5f * (fabsf(i00) + fabsf(i01)), ri = L_.ri + 0.5f * (fabsf(i10) + fabsf(i11));
+    const int wide = L_.wide;
+    __syncthreads();
+    if (x >= g.W || y >= g.H) return;
+    if (s_ok) {
+      const int JC = s_JC, IC = s_IC;
+      const float jcf = s_jcf, icf = s_icf;
+      // centre of this thread's 2 x 2 block relative to the CTA centre, and its pre-image relative to (JC, IC)
+      const float dxl = (float)(2 * tx) + 0.5f - 0.5f * kP2W, dyl = (float)(2 * ty) + 0.5f - 0.5f * kP2H;
+      const float pj = jcf + i00 * dxl + i01 * dyl, pi = icf + i10 * dxl + i11 * dyl;
+      const float mlo = fmaxf(ceilf(pj - rj), (float)(-JC)), mhi = fminf(floorf(pj + rj), (float)(g.W - 1 - JC));
+      const float nlo = fmaxf(ceilf(pi - ri), (float)(-IC)), nhi = fminf(floorf(pi + ri), (float)(g.H - 1 - IC));
+      if (mlo <= mhi && nlo <= nhi) {
+        const int m0 = (int)mlo, m1 = (int)mhi, n0 = (int)nlo, n1 = (int)nhi;
+        const float x0l = dxl - 0.5f, y0l = dyl - 0.5f;          // texel (0,0) of the block relative to the CTA centre
+        float di = nlo - icf;
+        const float2* recn = rec + (long long)n * hw + ((IC + n0) * g.W + JC);
+        const float4* gpb = gp + (long long)b * hw + ((IC + n0) * g.W + JC);
+        const float dj0 = mlo - jcf;
+        for (int nn = n0; nn <= n1; ++nn, di += 1.f, recn += g.W, gpb += g.W) {
+          const float ub = fmaf(a01, di, -x0l), vb = fmaf(a11, di, -y0l);
+          int ma = m0, mb = m1;
+          float dja = dj0;
+          if (wide) {
+            // magnifying or near-singular placement: solve |a00 dj + ub - kx| < 1, |a10 dj + vb - ky| < 1 for the
+            // row (dj = mm - jcf; kx, ky in {0, 1}) and keep one candidate of slack on either side
+            float lo = -3.0e9f, hi = 3.0e9f;
+            if (L_.r00 != 0.f) {
+              const float t0 = (-1.f - ub) * L_.r00, t1 = (2.f - ub) * L_.r00;
+              lo = fmaxf(lo, fminf(t0, t1)); hi = fminf(hi, fmaxf(t0, t1));
+            } else if (ub <= -1.f || ub >= 2.f) { hi = -3.0e9f; }
+            if (L_.r10 != 0.f) {
+              const float t0 = (-1.f - vb) * L_.r10, t1 = (2.f - vb) * L_.r10;
+              lo = fmaxf(lo, fminf(t0, t1)); hi = fminf(hi, fmaxf(t0, t1));
+            } else if (vb <= -1.f || vb >= 2.f) { hi = -3.0e9f; }
+            lo = fmaxf(floorf(lo + jcf) - 1.f, mlo);
+            hi = fminf(ceilf(hi + jcf) + 1.f, mhi);
+            if (!(lo <= hi)) continue;
+            ma = (int)lo; mb = (int)hi;
+            dja = lo - jcf;
+          }
+          float u = fmaf(a00, dja, ub);                          // ix(candidate) - x of texel column 0
+          float v = fmaf(a10, dja, vb);                          // iy(candidate) - y of texel row 0
 #pragma unroll 1
-        for (int mm = ma; mm <= mb; ++mm, u += a00, v += a10) {
-          const float wgt = fmaxf(1.f - fabsf(u), 0.f) * fmaxf(1.f - fabsf(v), 0.f);   // hat(u) hat(v)
-          const float2 r = __ldg(recn + mm);
-          const float4 G = __ldg(gpb + mm);
-          const float wt = wgt * r.x;
-          acc0 = fmaf(wt, G.x, acc0);
-          acc1 = fmaf(wt, G.y, acc1);
-          acc2 = fmaf(wt, G.z, acc2);
-          acc3 = fmaf(wgt, r.y, acc3);
+          for (int mm = ma; mm <= mb; ++mm, u += a00, v += a10) {
+            const float wx0 = hat(u), wx1 = hat(u - 1.f), wy0 = hat(v), wy1 = hat(v - 1.f);
+            const float2 r = __ldg(recn + mm);
+            const float4 G = __ldg(gpb + mm);
+            const f32x2 grg = pk(G.x * r.x, G.y * r.x), gba = pk(G.z * r.x, r.y);
+            const f32x2 w00 = bc(wy0 * wx0), w01 = bc(wy0 * wx1), w10 = bc(wy1 * wx0), w11 = bc(wy1 * wx1);
+            acc[0][0][0] = fma2(w00, grg, acc[0][0][0]); acc[0][0][1] = fma2(w00, gba, acc[0][0][1]);
+            acc[0][1][0] = fma2(w01, grg, acc[0][1][0]); acc[0][1][1] = fma2(w01, gba, acc[0][1][1]);
+            acc[1][0][0] = fma2(w10, grg, acc[1][0][0]); acc[1][0][1] = fma2(w10, gba, acc[1][0][1]);
+            acc[1][1][0] = fma2(w11, grg, acc[1][1][0]); acc[1][1][1] = fma2(w11, gba, acc[1][1][1]);
+          }
         }
       }
     }
   }
-  const float zs = g.m11 ? 0.5f : 1.f;          // d z / d x_texel = zs * weight
-  st(gxp, zs * acc0);
-  st(gxp + hw, zs * acc1);
-  st(gxp + 2 * hw, zs * acc2);
-  st(gxp + 3 * hw, zs * acc3);
+#pragma unroll
+  for (int ky = 0; ky < 2; ++ky) {
+    if (y + ky >= g.H) break;
+    float r0, g0, b0, a0, r1, g1, b1, a1;
+    upk(acc[ky][0][0], r0, g0); upk(acc[ky][0][1], b0, a0);
+    upk(acc[ky][1][0], r1, g1); upk(acc[ky][1][1], b1, a1);
+    T* o = gxp + ky * g.W;
+    Pack2<T>::store(o, zs * r0, zs * r1, two);
+    Pack2<T>::store(o + hw, zs * g0, zs * g1, two);
+    Pack2<T>::store(o + 2 * hw, zs * b0, zs * b1, two);
+    Pack2<T>::store(o + 3 * hw, zs * a0, zs * a1, two);
+  }
 }
 
 }  // namespace mgr

@@ -171,6 +171,9 @@ __device__ __forceinline__ void stage_footprint(const T* __restrict__ img, const
         const int r = r0 + it * kStageRows;
         const int y = p.y_lo + r;
         inside[it] = xin && r < p.bh && (unsigned)y < (unsigned)g.H;
+#ifdef MGR_EXPERIMENT_NO_STAGE_LOADS
+        inside[it] = false;
+#endif
         if (inside[it]) {
           const unsigned off = (unsigned)y * rowbytes + (unsigned)x * (unsigned)sizeof(T);
           R[it] = __ldg(reinterpret_cast<const Ld*>(base + off));
