@@ -112,4 +112,34 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Sum six per-lane values over the warp with a transposing butterfly: after the first three exchange steps each
+// lane carries one of eight partial sums (two are padding), so the whole reduction takes 9 shuffles instead of
+// 30.  On return, lane q * 4 (q = 0..5) holds the warp sum of v[q] in `out`; other lanes hold garbage.
+__device__ __forceinline__ float warp_sum6(const float (&v)[6], int lane) {
+  // step 1 (xor 16): lanes < 16 keep v0..v3 (index 0..3), lanes >= 16 keep v4, v5, 0, 0
+  const bool hi16 = lane & 16;
+  float a0 = hi16 ? v[4] : v[0], a1 = hi16 ? v[5] : v[1], a2 = hi16 ? 0.f : v[2], a3 = hi16 ? 0.f : v[3];
+  const float s0 = hi16 ? v[0] : v[4], s1 = hi16 ? v[1] : v[5], s2 = hi16 ? v[2] : 0.f, s3 = hi16 ? v[3] : 0.f;
+  a0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+  a1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  a2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+  a3 += __shfl_xor_sync(0xffffffffu, s3, 16);
+  // step 2 (xor 8): lanes with bit 3 clear keep a0, a1; set keep a2, a3
+  const bool hi8 = lane & 8;
+  float b0 = hi8 ? a2 : a0, b1 = hi8 ? a3 : a1;
+  const float t0 = hi8 ? a0 : a2, t1 = hi8 ? a1 : a3;
+  b0 += __shfl_xor_sync(0xffffffffu, t0, 8);
+  b1 += __shfl_xor_sync(0xffffffffu, t1, 8);
+  // step 3 (xor 4): bit 2 clear keeps b0, set keeps b1
+  const bool hi4 = lane & 4;
+  float c = hi4 ? b1 : b0;
+  const float w = hi4 ? b0 : b1;
+  c += __shfl_xor_sync(0xffffffffu, w, 4);
+  c += __shfl_xor_sync(0xffffffffu, c, 2);
+  c += __shfl_xor_sync(0xffffffffu, c, 1);
+  return c;     // lane bits (16, 8, 4) = (q >= 4, (q & 2) != 0, q & 1): value index q = 4*bit16 + 2*bit3 + bit2
+}
+// the value index held by a lane after warp_sum6 (0..7; 6 and 7 are padding)
+__device__ __forceinline__ int warp_sum6_index(int lane) { return ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1); }
+
 }  // namespace mgr

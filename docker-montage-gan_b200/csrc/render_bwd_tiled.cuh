@@ -30,7 +30,7 @@ namespace mgr {
 //   inverse plans [B*L] InverseLayer (128 B each)
 
 template <typename T, bool kNeedTheta>
-__global__ void __launch_bounds__(kTiledThreads, 2)
+__global__ void __launch_bounds__(kTiledThreads, 3)
 render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const T* __restrict__ out,
                  const T* __restrict__ gout, const typename SavedAlpha<T>::type* __restrict__ sav,
                  float2* __restrict__ rec, float4* __restrict__ gp, float* __restrict__ gtheta, Geometry g,
@@ -194,11 +194,9 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
     if (kNeedTheta) {
       // this thread's four pixels share the column: (ggx x_j, ggx y_i, ggx, ggy x_j, ggy y_i, ggy)
       float part[6] = {hW * accx * xj, hW * accxy, hW * accx, hH * accy * xj, hH * accyy, hH * accy};
-#pragma unroll
-      for (int q = 0; q < 6; ++q) {
-        const float s = warp_sum(part[q]);
-        if (tx == 0) atomicAdd(&gth_acc[l * 6 + q], s);
-      }
+      const float s = warp_sum6(part, tx);
+      const int q = warp_sum6_index(tx);
+      if ((tx & 3) == 0 && q < 6) atomicAdd(&gth_acc[l * 6 + q], s);
     }
   }
   if (kNeedTheta) {
@@ -216,6 +214,7 @@ struct InverseLayer {
   double i00, i01, i10, i11;    // A^-1, pixel space
   double c0, c1;                // (ix, iy) = A (j, i) + c
   float a00, a01, a10, a11;     // A
+  float f00, f01, f10, f11;     // A^-1 rounded to fp32 (per-thread use)
   float rj, ri;                 // half extents of the pre-image of a texel's (-1,1)^2 support (+ slack)
   float r00, r10;               // 1/a00, 1/a10 (0 if ~0): per-row interval refinement for wide windows
   int valid;                    // 0: non-finite or singular placement -> grad_x of this layer is 0
@@ -240,6 +239,7 @@ static __global__ void inverse_plans_kernel(const float* __restrict__ theta, Inv
   const double inv = 1.0 / (a00 * a11 - a01 * a10);
   q.i00 = a11 * inv; q.i01 = -a01 * inv; q.i10 = -a10 * inv; q.i11 = a00 * inv;
   q.a00 = (float)a00; q.a01 = (float)a01; q.a10 = (float)a10; q.a11 = (float)a11;
+  q.f00 = (float)q.i00; q.f01 = (float)q.i01; q.f10 = (float)q.i10; q.f11 = (float)q.i11;
   const double rj = fabs(q.i00) + fabs(q.i01), ri = fabs(q.i10) + fabs(q.i11);
   q.valid = isfinite(q.c0) && isfinite(q.c1) && isfinite(rj) && isfinite(ri) && rj < 1.0e6 && ri < 1.0e6;
   q.rj = (float)rj * 1.0001f + 1e-3f; q.ri = (float)ri * 1.0001f + 1e-3f;
@@ -268,20 +268,20 @@ static __global__ void sample_flags_kernel(InverseLayer* __restrict__ plans, int
 // record loads and the per-candidate coordinate arithmetic; the accumulators are packed fp32x2 pairs.
 constexpr int kP2W = 64, kP2H = 16;
 
-template <typename T> struct Pack2;      // two horizontally adjacent texels of one channel -> one store
+template <typename T> struct Pack2;      // two horizontally adjacent texels of one channel -> one (aligned) store
 template <> struct Pack2<float> {
-  __device__ static __forceinline__ void store(float* p, float a, float b, bool two) {
-    if (two) *reinterpret_cast<float2*>(p) = make_float2(a, b); else *p = a;
+  __device__ static __forceinline__ void store(float* p, float a, float b) {
+    *reinterpret_cast<float2*>(p) = make_float2(a, b);
   }
 };
 template <> struct Pack2<__nv_bfloat16> {
-  __device__ static __forceinline__ void store(__nv_bfloat16* p, float a, float b, bool two) {
-    if (two) *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); else *p = __float2bfloat16_rn(a);
+  __device__ static __forceinline__ void store(__nv_bfloat16* p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b);
   }
 };
 template <> struct Pack2<__half> {
-  __device__ static __forceinline__ void store(__half* p, float a, float b, bool two) {
-    if (two) *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b); else *p = __float2half_rn(a);
+  __device__ static __forceinline__ void store(__half* p, float a, float b) {
+    *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b);
   }
 };
 
@@ -303,7 +303,6 @@ render_bwd_pass2(const InverseLayer* __restrict__ plans, const float2* __restric
   const int x = x0b + 2 * tx, y = y0b + 2 * ty;                // top-left texel of this thread's 2 x 2 block
   const float zs = g.m11 ? 0.5f : 1.f;          // d z / d x_texel = zs * weight
   T* gxp = gx + (long long)n * 4 * hw + y * g.W + x;
-  const bool two = x + 1 < g.W;                 // W is even on this path (tiled_ok), kept for safety
   f32x2 acc[2][2][2];                           // [row][col][rg | ba]
 #pragma unroll
   for (int q = 0; q < 8; ++q) (&acc[0][0][0])[q] = 0ull;
@@ -353,7 +352,7 @@ render_bwd_pass2(const InverseLayer* __restrict__ plans, const float2* __restric
       s_ok = ok;
     }
     const float a00 = L_.a00, a01 = L_.a01, a10 = L_.a10, a11 = L_.a11;
-    const float i00 = (float)L_.i00, i01 = (float)L_.i01, i10 = (float)L_.i10, i11 = (float)L_.i11;
+    const float i00 = L_.f00, i01 = L_.f01, i10 = L_.f10, i11 = L_.f11;
     // half extents of the pre-image of the 2 x 2 block's support: a texel's (-1,1)^2 grown by +-0.5
     const float rj = L_.rj + 0.5f * (fabsf(i00) + fabsf(i01)), ri = L_.ri + 0.5f * (fabsf(i10) + fabsf(i11));
     const int wide = L_.wide;
@@ -421,10 +420,10 @@ render_bwd_pass2(const InverseLayer* __restrict__ plans, const float2* __restric
     upk(acc[ky][0][0], r0, g0); upk(acc[ky][0][1], b0, a0);
     upk(acc[ky][1][0], r1, g1); upk(acc[ky][1][1], b1, a1);
     T* o = gxp + ky * g.W;
-    Pack2<T>::store(o, zs * r0, zs * r1, two);
-    Pack2<T>::store(o + hw, zs * g0, zs * g1, two);
-    Pack2<T>::store(o + 2 * hw, zs * b0, zs * b1, two);
-    Pack2<T>::store(o + 3 * hw, zs * a0, zs * a1, two);
+    Pack2<T>::store(o, zs * r0, zs * r1);              // W % 4 == 0 on this path: x + 1 < W
+    Pack2<T>::store(o + hw, zs * g0, zs * g1);
+    Pack2<T>::store(o + 2 * hw, zs * b0, zs * b1);
+    Pack2<T>::store(o + 3 * hw, zs * a0, zs * a1);
   }
 }
 

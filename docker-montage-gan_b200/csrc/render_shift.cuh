@@ -301,11 +301,9 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
     }
     if (kNeedTheta) {
       float part[6] = {hW * accx * xj, hW * accxy, hW * accx, hH * accy * xj, hH * accyy, hH * accy};
-#pragma unroll
-      for (int qq = 0; qq < 6; ++qq) {
-        const float s = warp_sum(part[qq]);
-        if (tx == 0) atomicAdd(&gth_acc[l * 6 + qq], s);
-      }
+      const float s = warp_sum6(part, tx);
+      const int qq = warp_sum6_index(tx);
+      if ((tx & 3) == 0 && qq < 6) atomicAdd(&gth_acc[l * 6 + qq], s);
     }
     if (kNeedX) {
       __syncthreads();                                        // records of the whole tile are in G
