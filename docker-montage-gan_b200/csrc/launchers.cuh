@@ -218,6 +218,16 @@ int launch_pad_stack(const void* src, const long long* ss, void* dst, int B, int
   return MGR_OK;
 }
 
+template <typename T>
+int launch_composite_jvp(const void* x, const void* tx, void* tout, const Geometry& g, cudaStream_t s) {
+  const long long total = (long long)g.B * g.H * g.W;
+  const long long blocks = (total + 255) / 256;
+  composite_jvp_kernel<T><<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, s>>>((const T*)x, (const T*)tx, (T*)tout, g);
+  MGR_CUDA(cudaGetLastError());
+  count_launch();
+  return MGR_OK;
+}
+
 }  // namespace mgr
 
 #include "launchers_decl.h"
@@ -240,4 +250,7 @@ int launch_pad_stack(const void* src, const long long* ss, void* dst, int B, int
   int mgr_pad_stack_##SUFFIX(const void* src, const long long* ss, void* dst, int B, int L, int l, int h,    \
                              int w, int H, int W, float pad, cudaStream_t s) {                               \
     return mgr::launch_pad_stack<T>(src, ss, dst, B, L, l, h, w, H, W, pad, s);                              \
+  }                                                                                                          \
+  int mgr_jvp_##SUFFIX(const void* x, const void* tx, void* tout, const mgr::Geometry& g, cudaStream_t s) {  \
+    return mgr::launch_composite_jvp<T>(x, tx, tout, g, s);                                                  \
   }

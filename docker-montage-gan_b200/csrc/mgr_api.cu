@@ -211,6 +211,20 @@ int mgr_pad_stack_layer(const void* src, const int64_t* src_strides, void* dst, 
 }
 
 
+int mgr_composite_jvp(const void* x, const int64_t* x_strides, const void* tangent, void* out_tangent, int B, int L,
+                      int H, int W, int dtype, int range_mode, void* stream) {
+  mgr::Geometry g;
+  if (int rc = check_common(x, x_strides, B, L, H, W, dtype, range_mode, &g)) return rc;
+  if (!tangent || !out_tangent) return fail(MGR_ERR_INVALID_ARGUMENT, "tangent / out_tangent is NULL");
+  if (B == 0) return MGR_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case MGR_F32: return mgr_jvp_f32(x, tangent, out_tangent, g, s);
+    case MGR_BF16: return mgr_jvp_bf16(x, tangent, out_tangent, g, s);
+    default: return mgr_jvp_f16(x, tangent, out_tangent, g, s);
+  }
+}
+
 // ---- end-to-end entry point with HOST buffers: chunked, double-buffered, three streams ----------------
 namespace {
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }

@@ -30,7 +30,7 @@ namespace mgr {
 //   inverse plans [B*L] InverseLayer (128 B each)
 
 template <typename T, bool kNeedTheta>
-__global__ void __launch_bounds__(kTiledThreads, 3)
+__global__ void __launch_bounds__(kTiledThreads, 2)
 render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const T* __restrict__ out,
                  const T* __restrict__ gout, const typename SavedAlpha<T>::type* __restrict__ sav,
                  float2* __restrict__ rec, float4* __restrict__ gp, float* __restrict__ gtheta, Geometry g,

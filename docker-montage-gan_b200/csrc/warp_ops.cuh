@@ -127,4 +127,49 @@ __global__ void pad_stack_kernel(const T* __restrict__ src, long long ssb, long 
   }
 }
 
+// ---- forward-mode derivative (JVP) of the composite: d out along a tangent of x ------------------------
+// Needed for the double backward of the composite-only branch (R1 penalty on the real layers,
+// custom/loss_aio.py:327-338): the backward is linear in grad_out, so its adjoint w.r.t. grad_out is this JVP.
+//   S' = a' c + a c' - a' S + (1-a) S',  R' = a' - a' R + (1-a) R'  (back -> front),  o = S/R:
+//   o'_rgb = S'/R - S R'/R^2 (0 where R == 0),  o'_a = R'
+template <typename T>
+__global__ void composite_jvp_kernel(const T* __restrict__ x, const T* __restrict__ tx, T* __restrict__ tout, Geometry g) {
+  const long long hw = (long long)g.H * g.W;
+  const long long total = (long long)g.B * hw;
+  const float zs = g.m11 ? 0.5f : 1.f, zb = g.m11 ? 0.5f : 0.f;   // z = zs x + zb, z' = zs x', out' = o' / zs
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+    const long long b = k / hw, pix = k - b * hw;
+    const int i = (int)(pix / g.W), j = (int)(pix - (long long)i * g.W);
+    const T* xb = x + b * g.sb + (long long)i * g.sh + j;
+    const T* tb = tx + (b * g.L * 4) * hw + pix;               // tangent is contiguous
+    float S[3] = {0.f, 0.f, 0.f}, dS[3] = {0.f, 0.f, 0.f}, R = 0.f, dR = 0.f;
+    float c[3] = {0.f, 0.f, 0.f}, dc[3] = {0.f, 0.f, 0.f}, a = 0.f, da = 0.f;
+    for (int l = 0; l < g.L; ++l) {
+      const T* xl = xb + (long long)l * g.sl;
+      const T* tl = tb + (long long)l * 4 * hw;
+      a = fmaf(ld(xl + 3 * g.sc), zs, zb); da = zs * ld(tl + 3 * hw);
+#pragma unroll
+      for (int q = 0; q < 3; ++q) {
+        c[q] = fmaf(ld(xl + q * g.sc), zs, zb); dc[q] = zs * ld(tl + q * hw);
+        dS[q] = da * (c[q] - S[q]) + a * dc[q] + (1.f - a) * dS[q];
+        S[q] = fmaf(1.f - a, S[q], a * c[q]);
+      }
+      dR = da * (1.f - R) + (1.f - a) * dR;
+      R = fmaf(1.f - a, R, a);
+    }
+    const float os = g.m11 ? 2.f : 1.f;                         // out = os o + const
+    T* o = tout + b * 4 * hw + pix;
+    if (g.L == 1) {                                             // single layer is returned untouched
+#pragma unroll
+      for (int q = 0; q < 3; ++q) st(o + q * hw, os * dc[q]);
+      st(o + 3 * hw, os * da);
+    } else {
+      const float inv = (R != 0.f) ? 1.f / R : 0.f;
+#pragma unroll
+      for (int q = 0; q < 3; ++q) st(o + q * hw, os * (dS[q] - S[q] * inv * dR) * inv);
+      st(o + 3 * hw, os * dR);
+    }
+  }
+}
+
 }  // namespace mgr

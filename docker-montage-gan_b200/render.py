@@ -86,31 +86,69 @@ class _Render(torch.autograd.Function):
         return out
 
     @staticmethod
-    @torch.autograd.function.once_differentiable
     def backward(ctx, grad_out):
-        lib = _lib.load()
         xk, th, out, sav = ctx.saved_tensors
-        B, L, _, H, W = xk.shape
         need_x = ctx.needs_input_grad[0]
         need_t = th is not None and ctx.needs_input_grad[1]
-        flags = (_lib.MGR_NEED_GRAD_X if need_x else 0) | (_lib.MGR_NEED_GRAD_THETA if need_t else 0)
-        if flags == 0:
+        if not (need_x or need_t):
             return None, None, None
-        go = grad_out.to(xk.dtype).contiguous()
-        gx = torch.empty((B, L, 4, H, W), dtype=xk.dtype, device=xk.device) if need_x else None
-        gt = torch.empty((B, L, 2, 3), dtype=torch.float32, device=xk.device) if need_t else None
-        dt = _DTYPES[xk.dtype]
-        ws_bytes = lib.mgr_render_backward_workspace_bytes(B, L, H, W, dt, int(th is not None), flags)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xk.device) if ws_bytes else None
-        with torch.cuda.device(xk.device):
-            rc = lib.mgr_render_backward(_ptr(xk), ctx.x_strides, _ptr(th), _ptr(out), _ptr(go), _ptr(sav), _ptr(gx), _ptr(gt),
-                                         _ptr(ws), ws_bytes, B, L, H, W, dt, _RANGES[ctx.in_range], flags,
-                                         _stream_ptr(xk.device))
-        _lib.check(rc, "mgr_render_backward")
-        _lib.launch_count += 1
+        if th is None:
+            # composite only (the real-image branch): a Function of its own so that it can be differentiated
+            # again w.r.t. grad_out -- the R1 penalty needs that (custom/loss_aio.py:327-338)
+            return _CompositeBackward.apply(grad_out, xk, out, ctx.in_range, ctx.x_strides), None, None
+        if torch.is_grad_enabled() and grad_out.requires_grad:
+            raise NotImplementedError("double backward through the warp is not implemented (only the composite-only "
+                                      "path, theta=None, is twice differentiable)")
+        gx, gt = _render_backward(xk, th, out, sav, grad_out, ctx.in_range, ctx.x_strides, need_x, need_t)
         if gt is not None and ctx.theta_dtype != torch.float32:
             gt = gt.to(ctx.theta_dtype)
         return gx, gt, None
+
+
+def _render_backward(xk, th, out, sav, grad_out, in_range, x_strides, need_x, need_t):
+    lib = _lib.load()
+    B, L, _, H, W = xk.shape
+    flags = (_lib.MGR_NEED_GRAD_X if need_x else 0) | (_lib.MGR_NEED_GRAD_THETA if need_t else 0)
+    go = grad_out.detach().to(xk.dtype).contiguous()
+    gx = torch.empty((B, L, 4, H, W), dtype=xk.dtype, device=xk.device) if need_x else None
+    gt = torch.empty((B, L, 2, 3), dtype=torch.float32, device=xk.device) if need_t else None
+    dt = _DTYPES[xk.dtype]
+    ws_bytes = lib.mgr_render_backward_workspace_bytes(B, L, H, W, dt, int(th is not None), flags)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xk.device) if ws_bytes else None
+    with torch.cuda.device(xk.device):
+        rc = lib.mgr_render_backward(_ptr(xk), x_strides, _ptr(th), _ptr(out), _ptr(go), _ptr(sav), _ptr(gx), _ptr(gt),
+                                     _ptr(ws), ws_bytes, B, L, H, W, dt, _RANGES[in_range], flags, _stream_ptr(xk.device))
+    _lib.check(rc, "mgr_render_backward")
+    _lib.launch_count += 1
+    return gx, gt
+
+
+class _CompositeBackward(torch.autograd.Function):
+    """grad_x = J(x)^T grad_out for the composite; linear in grad_out, so its own backward w.r.t. grad_out is
+    the JVP J(x) v (pattern: the reference's hand-written second-order ops, torch_utils/ops/bias_act.py:198-226,
+    grid_sample_gradfix.py:68-88).  The second-order term w.r.t. x is not provided (nothing in the reference's
+    losses uses it: the real layers are data)."""
+
+    @staticmethod
+    def forward(ctx, grad_out, xk, out, in_range, x_strides):
+        gx, _ = _render_backward(xk, None, out, None, grad_out, in_range, x_strides, True, False)
+        ctx.save_for_backward(xk)
+        ctx.in_range, ctx.x_strides, ctx.go_dtype = in_range, x_strides, grad_out.dtype
+        return gx
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, v):
+        lib = _lib.load()
+        (xk,) = ctx.saved_tensors
+        B, L, _, H, W = xk.shape
+        vt = v.to(xk.dtype).contiguous()
+        jv = torch.empty((B, 4, H, W), dtype=xk.dtype, device=xk.device)
+        with torch.cuda.device(xk.device):
+            rc = lib.mgr_composite_jvp(_ptr(xk), ctx.x_strides, _ptr(vt), _ptr(jv), B, L, H, W, _DTYPES[xk.dtype],
+                                       _RANGES[ctx.in_range], _stream_ptr(xk.device))
+        _lib.check(rc, "mgr_composite_jvp")
+        return jv.to(ctx.go_dtype), None, None, None, None
 
 
 def render(x: torch.Tensor, theta: torch.Tensor | None = None, *, in_range: str = "m11") -> torch.Tensor:

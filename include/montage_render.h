@@ -152,6 +152,15 @@ int mgr_pad_stack_layer(const void* src, const int64_t* src_strides, void* dst, 
                         int h, int w, int H, int W, float pad_value, int dtype, void* stream);
 
 /*
+ * Forward-mode derivative of the composite (theta == NULL path): out_tangent [B,4,H,W] = d out along
+ * `tangent` [B,L,4,H,W] (contiguous) at x.  This is the double backward of the composite w.r.t. grad_out,
+ * which the global discriminator's R1 penalty on the real layers needs (custom/loss_aio.py:327-338; the
+ * reference gets it from stock autograd, its own plugins provide it by hand: torch_utils/ops/bias_act.py:198-226).
+ */
+int mgr_composite_jvp(const void* x, const int64_t* x_strides, const void* tangent, void* out_tangent,
+                      int B, int L, int H, int W, int dtype, int range_mode, void* stream);
+
+/*
  * End to end with HOST buffers: out, grad_x, grad_theta = fwd+bwd(x, theta, grad_out), everything in
  * (preferably pinned) host memory, laid out exactly like the device tensors.  The batch is cut
  * into chunks of chunk_B samples that flow through two device slots on three streams (H2D copy,

@@ -467,3 +467,41 @@ def test_stencil_kernels_match_general_kernels(dtype):
     assert rel_err(res[0][1], res[1][1]) <= (2e-5 if f32 else 2 ** -6)
     assert rel_err(res[0][2], res[1][2]) <= (2e-3 if f32 else 5e-2)
     assert np.array_equal(res[0][0][1], res[1][0][1])          # the general sample is bit-identical either way
+
+
+def test_r1_double_backward_on_the_real_branch():
+    """The global discriminator's R1 penalty on real layers (custom/loss_aio.py:327-338): composite only,
+    grad of logits w.r.t. the layers with create_graph=True, then backward of its squared norm.  D's weights
+    see the penalty only through the composite's double backward w.r.t. grad_out (a JVP)."""
+    B, L, H, W = 2, 5, 24, 24
+    x = synth.make_layers(B, L, H, W, "W", seed=41)
+    wgt = torch.randn(B, 4, H, W, generator=torch.Generator().manual_seed(41))
+
+    def penalty(render_fn, x_, w_):
+        x_ = x_.detach().requires_grad_(True)
+        w_ = w_.detach().requires_grad_(True)
+        logits = (render_fn(x_) * w_).sum()                    # stand-in for D: linear in the composite, weights w_
+        (g,) = torch.autograd.grad(logits, x_, create_graph=True)
+        pen = g.square().sum()
+        pen.backward()
+        return pen.detach(), w_.grad.detach()
+
+    p_ref, gw_ref = penalty(lambda t: TC.port_chain(t, None, "m11"), x.double(), wgt.double())
+    p_new, gw_new = penalty(lambda t: mr.render(t, None), x.to(DEV), wgt.to(DEV))
+    assert abs(p_new.item() - p_ref.item()) / abs(p_ref.item()) < 1e-5
+    assert rel_err(gw_new.cpu().numpy(), gw_ref.numpy()) < 1e-4
+    # the JVP itself against the oracle
+    v = torch.randn(B, L, 4, H, W, generator=torch.Generator().manual_seed(42))
+    z = (x.double().numpy() + 1) / 2
+    ref = 2 * R.composite_jvp(z, v.double().numpy() * 0.5)       # chain rule for the m11 range shifts
+    xs = x.to(DEV).requires_grad_(True)
+    go = torch.zeros(B, 4, H, W, device=DEV, requires_grad=True)
+    out = mr.render(xs, None)
+    (gx,) = torch.autograd.grad(out, xs, go, create_graph=True)
+    (jv,) = torch.autograd.grad(gx, go, v.to(DEV))
+    assert max_abs(jv.cpu().numpy(), ref) < 1e-4 * max(1.0, float(np.abs(ref).max()))
+    # the warp path is once differentiable and says so
+    th = synth.make_theta(B, L, "I", seed=41).to(DEV)
+    out = mr.render(xs, th)
+    with pytest.raises(NotImplementedError):
+        torch.autograd.grad(out, xs, go, create_graph=True)
