@@ -103,8 +103,9 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
       configured = true;
     }
     if (nt) MGR_CUDA(cudaMemsetAsync(gtheta, 0, sizeof(float) * 6 * g.B * g.L, s));
-    const size_t smem = tiled_smem_bytes(g.L, sizeof(Vec)) + sizeof(float) * 6 * g.L +
-                        sizeof(float) * (size_t)g.L * kPx * kTiledThreads;          // + transmittance stash
+    const size_t smem = tiled_smem_bytes(g.L, sizeof(Vec)) + sizeof(float) * ((6 * g.L + 3) & ~3) +
+                        sizeof(float) * (size_t)g.L * kPx * kTiledThreads +         // + transmittance stash
+                        sizeof(float4) * kPx * kTiledThreads;                       // + (G_P, G_A) per pixel
     dim3 grid((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B);
     const int shift = debug_path() != 2;
     if (nt)

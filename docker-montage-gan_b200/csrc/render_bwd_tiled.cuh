@@ -30,7 +30,7 @@ namespace mgr {
 //   inverse plans [B*L] InverseLayer (128 B each)
 
 template <typename T, bool kNeedTheta>
-__global__ void __launch_bounds__(kTiledThreads, 2)
+__global__ void __launch_bounds__(kTiledThreads, 3)
 render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const T* __restrict__ out,
                  const T* __restrict__ gout, const typename SavedAlpha<T>::type* __restrict__ sav,
                  float2* __restrict__ rec, float4* __restrict__ gp, float* __restrict__ gtheta, Geometry g,
@@ -41,7 +41,9 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
   LayerPlan* plan = reinterpret_cast<LayerPlan*>(smem_raw + sizeof(Vec) * kCapTexels);    // [L]
   float* gth_acc = reinterpret_cast<float*>(plan + g.L);                                  // [L][6]
   const int tid = threadIdx.x;
-  float* Tst = gth_acc + 6 * g.L + tid;                     // [L][kPx][256]: transmittance in front of layer l
+  const int gth_pad = (6 * g.L + 3) & ~3;                   // keep the arrays behind it 16-byte aligned
+  float* Tst = gth_acc + gth_pad + tid;                     // [L][kPx][256]: transmittance in front of layer l
+  float4* GPs = reinterpret_cast<float4*>(gth_acc + gth_pad + (size_t)g.L * kPx * kTiledThreads) + tid;   // [kPx][256]: (G_P, G_A)
   const int b = blockIdx.z;
   if (skip_shift && cta_all_shift(theta + (long long)b * g.L * 6, g.L, tid, kTiledThreads)) return;   // render_bwd_shift's
   const int j0 = blockIdx.x * kTW, i0 = blockIdx.y * kTH;
@@ -66,8 +68,8 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
   const typename SavedAlpha<T>::type* savb = sav + (long long)b * g.L * hw + pix0;
 
   // ---- pre-pass: T_l (stashed in shared memory) and A ------------------------------------------------
-  float GP0[kPx], GP1[kPx], GP2[kPx], GA[kPx];
   {
+    float GP0[kPx], GP1[kPx], GP2[kPx], GA[kPx];
     float Tc[kPx], A[kPx];
 #pragma unroll
     for (int k = 0; k < kPx; ++k) { Tc[k] = 1.f; A[k] = 0.f; }
@@ -102,6 +104,7 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
         }
         gp[(long long)b * hw + pix0 + k * row8] = make_float4(GP0[k], GP1[k], GP2[k], 0.f);
       }
+      GPs[k * kTiledThreads] = make_float4(GP0[k], GP1[k], GP2[k], GA[k]);
     }
   }
 
@@ -123,7 +126,8 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
         if (live[k]) {
           const float T_l = Tst[(l * kPx + k) * kTiledThreads];
           // c_l = 0 in the compositing domain (transparent black)
-          const float ga = T_l * (-(GP0[k] * S0[k] + GP1[k] * S1[k] + GP2[k] * S2[k]) + GA[k] * (1.f - R[k]));
+          const float4 G4 = GPs[k * kTiledThreads];
+          const float ga = T_l * (-(G4.x * S0[k] + G4.y * S1[k] + G4.z * S2[k]) + G4.w * (1.f - R[k]));
           rl[k * row8] = make_float2(0.f, ga);
         }
       }
@@ -175,10 +179,11 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
       }
       const float T_l = Tst[(l * kPx + k) * kTiledThreads];
       const float ta = T_l * a;
-      const float ga = T_l * (GP0[k] * (r_ - S0[k]) + GP1[k] * (g_ - S1[k]) + GP2[k] * (b_ - S2[k]) + GA[k] * (1.f - R[k]));
+      const float4 G4 = GPs[k * kTiledThreads];
+      const float ga = T_l * (G4.x * (r_ - S0[k]) + G4.y * (g_ - S1[k]) + G4.z * (b_ - S2[k]) + G4.w * (1.f - R[k]));
       if (live[k]) rl[k * row8] = make_float2(ta, ga);
       if (kNeedTheta) {
-        const float gr = GP0[k] * ta, gg = GP1[k] * ta, gb = GP2[k] * ta;
+        const float gr = G4.x * ta, gg = G4.y * ta, gb = G4.z * ta;
         const float dix = fmaf(gr, dxr, fmaf(gg, dxg, fmaf(gb, dxb, ga * dxa)));
         const float diy = fmaf(gr, dyr, fmaf(gg, dyg, fmaf(gb, dyb, ga * dya)));
         const float yi = norm_coord(i0 + ty + kRowStep * k, g.H);
