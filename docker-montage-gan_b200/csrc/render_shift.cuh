@@ -152,7 +152,7 @@ inline size_t shift_fwd_smem_bytes(int L, size_t vec_bytes) { return vec_bytes *
 constexpr int kAnchor = kTW - 1;
 
 template <typename T, bool kNeedX, bool kNeedTheta>
-__global__ void __launch_bounds__(kTiledThreads, 2)
+__global__ void __launch_bounds__(kTiledThreads, 3)
 render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const T* __restrict__ out,
                  const T* __restrict__ gout, const typename SavedAlpha<T>::type* __restrict__ sav,
                  T* __restrict__ gx, float* __restrict__ gtheta, Geometry g) {
@@ -163,7 +163,9 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
   ShiftPlan* splan = reinterpret_cast<ShiftPlan*>(G + kTW * kTH);                        // [L]
   float* gth_acc = reinterpret_cast<float*>(splan + g.L);                                // [L][6]
   const int tid = threadIdx.x;
-  float* Tst = gth_acc + 6 * g.L + tid;                                                  // [L][kPx][256]
+  const int gth_pad = (6 * g.L + 3) & ~3;
+  float* Tst = gth_acc + gth_pad + tid;                                                  // [L][kPx][256]
+  float4* GPs = reinterpret_cast<float4*>(gth_acc + gth_pad + (size_t)g.L * kPx * kTiledThreads) + tid;   // [kPx][256]
   const int b = blockIdx.z;
   const float* thb = theta + (long long)b * g.L * 6;
   if (!cta_all_shift(thb, g.L, tid, kTiledThreads)) return;
@@ -193,8 +195,8 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
   const typename SavedAlpha<T>::type* savb = sav + (long long)b * g.L * hw + pix0;
 
   // ---- pre-pass: T_l and A from the saved alpha samples ---------------------------------------------
-  float GP0[kPx], GP1[kPx], GP2[kPx], GA[kPx];
   {
+    float GP0[kPx], GP1[kPx], GP2[kPx], GA[kPx];
     float Tc[kPx], A[kPx];
 #pragma unroll
     for (int k = 0; k < kPx; ++k) { Tc[k] = 1.f; A[k] = 0.f; }
@@ -226,6 +228,7 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
           GA[k] = g3 - (g0 * o0 + g1 * o1 + g2 * o2) * inv;
         }
       }
+      GPs[k * kTiledThreads] = make_float4(GP0[k], GP1[k], GP2[k], GA[k]);
     }
   }
 
@@ -239,11 +242,31 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
   for (int l = 0; l < g.L; ++l) {
     const ShiftPlan sp = splan[l];
     const LayerPlan p = shift_footprint(sp, j0, i0, g.H, g.W);
+    if (p.mode == kSkip) {
+      // the footprint misses the image: a transparent-black layer for this tile (a = 0): the canvas is unchanged,
+      // no theta gradient, and none of this tile's anchor texels lies inside the image.  What remains is to zero
+      // the texels at this tile's own (unshifted) coordinates that no pixel touches.
+      if (kNeedX) {
+        T* gxl = gx + ((long long)b * g.L + l) * 4 * hw;
+#pragma unroll
+        for (int k = 0; k < kPx; ++k) {
+          const int brow = ibase + k;
+          if (tx >= 1 && (kPx * ty + k) >= 1 && j < g.W && brow < g.H) {
+            const int pa = j - sp.X, pb = brow - sp.Y;
+            if (pa < 0 || pa > g.W || pb < 0 || pb > g.H) {
+              T* o = gxl + brow * g.W + j;
+              st(o, 0.f); st(o + hw, 0.f); st(o + 2 * hw, 0.f); st(o + 3 * hw, 0.f);
+            }
+          }
+        }
+      }
+      continue;
+    }
     __syncthreads();                                          // previous layer: buf readers and G readers are done
-    if (p.mode == kStaged) stage_footprint<T>(xb + (long long)l * g.sl, g, p, buf, tid);
+    stage_footprint<T>(xb + (long long)l * g.sl, g, p, buf, tid);
     __syncthreads();
     float accx = 0.f, accxy = 0.f, accy = 0.f, accyy = 0.f;
-    if (p.mode == kStaged) {
+    {
       const f32x2 fx2 = bc(sp.fx), fy2 = bc(sp.fy);
       const Vec* q = buf + (kPx * ty) * p.bw + (tx + j0 + sp.X - p.x_lo);
       f32x2 h_rg, h_ba, d_rg, d_ba;                           // row: lerped value and horizontal difference
@@ -270,8 +293,9 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
         h_rg = n_rg; h_ba = n_ba; d_rg = e_rg; d_ba = e_ba;
         const float T_l = Tst[(l * kPx + k) * kTiledThreads];
         const float ta = T_l * a;
-        const float ga = T_l * (GP0[k] * (r_ - S0[k]) + GP1[k] * (g_ - S1[k]) + GP2[k] * (b_ - S2[k]) + GA[k] * (1.f - R[k]));
-        const float gr = GP0[k] * ta, gg = GP1[k] * ta, gb = GP2[k] * ta;
+        const float4 G4 = GPs[k * kTiledThreads];
+        const float ga = T_l * (G4.x * (r_ - S0[k]) + G4.y * (g_ - S1[k]) + G4.z * (b_ - S2[k]) + G4.w * (1.f - R[k]));
+        const float gr = G4.x * ta, gg = G4.y * ta, gb = G4.z * ta;
         if (kNeedX) Gt[k * kTW] = make_float4(gr, gg, gb, ga);
         if (kNeedTheta) {
           float dxr, dxg, dxb, dxa, dyr, dyg, dyb, dya;
@@ -290,13 +314,6 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
         S1[k] = fmaf(om, S1[k], a * g_);
         S2[k] = fmaf(om, S2[k], a * b_);
         R[k] = fmaf(om, R[k], a);
-      }
-    } else {
-      // the footprint misses the image: transparent black layer (a = 0, c = 0); d a_l is still defined but
-      // no texel receives anything
-      if (kNeedX) {
-#pragma unroll
-        for (int k = 0; k < kPx; ++k) Gt[k * kTW] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     if (kNeedTheta) {
@@ -356,8 +373,8 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
 }
 
 inline size_t shift_bwd_smem_bytes(int L, size_t vec_bytes) {
-  return vec_bytes * kShiftCap + sizeof(float4) * kTW * kTH + sizeof(ShiftPlan) * L + sizeof(float) * 6 * L +
-         sizeof(float) * (size_t)L * kPx * kTiledThreads;
+  return vec_bytes * kShiftCap + sizeof(float4) * kTW * kTH + sizeof(ShiftPlan) * L + sizeof(float) * ((6 * L + 3) & ~3) +
+         sizeof(float) * (size_t)L * kPx * kTiledThreads + sizeof(float4) * kPx * kTiledThreads;
 }
 
 }  // namespace mgr
