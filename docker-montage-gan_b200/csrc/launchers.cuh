@@ -96,6 +96,7 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
     float2* rec = reinterpret_cast<float2*>(ws);
     float4* gp = reinterpret_cast<float4*>(reinterpret_cast<char*>(ws) + sizeof(float2) * (size_t)g.B * g.L * g.H * g.W);
     InverseLayer* inv = reinterpret_cast<InverseLayer*>(reinterpret_cast<char*>(gp) + sizeof(float4) * (size_t)g.B * g.H * g.W);
+    int* order = reinterpret_cast<int*>(inv + (size_t)g.B * g.L);          // [B*L] + 2 counters
     static bool configured = false;
     if (!configured) {
       MGR_CUDA(cudaFuncSetAttribute(render_bwd_pass1<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -118,11 +119,12 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
     count_launch();
     if (nx) {
       dim3 grid2((g.W + kP2W - 1) / kP2W, (g.H + kP2H - 1) / kP2H, g.B * g.L);
-      inverse_plans_kernel<<<(g.B * g.L + 127) / 128, 128, 0, s>>>(theta, inv, g.B * g.L, g.H, g.W);
+      MGR_CUDA(cudaMemsetAsync(order + g.B * g.L, 0, 2 * sizeof(int), s));
+      inverse_plans_kernel<<<(g.B * g.L + 127) / 128, 128, 0, s>>>(theta, inv, g.B * g.L, g.H, g.W, order, order + g.B * g.L);
       sample_flags_kernel<<<(g.B + 127) / 128, 128, 0, s>>>(inv, g.B, g.L);
       MGR_CUDA(cudaGetLastError());
       count_launch(2);
-      render_bwd_pass2<T><<<grid2, 256, 0, s>>>(inv, rec, gp, (T*)gx, g, shift);
+      render_bwd_pass2<T><<<grid2, 256, 0, s>>>(inv, order, rec, gp, (T*)gx, g, shift);
       MGR_CUDA(cudaGetLastError());
       count_launch();
     }

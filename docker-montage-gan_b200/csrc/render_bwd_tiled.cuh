@@ -27,7 +27,7 @@ namespace mgr {
 
 // workspace layout of the tiled backward (all fp32):
 //   rec [B*L][H*W] float2 = (T_l a_l, d a_l)        gp [B][H*W] float4 = (G_P.rgb, unused)
-//   inverse plans [B*L] InverseLayer (128 B each)
+//   inverse plans [B*L] InverseLayer (128 B each)        order [B*L] int + 2 counters
 
 template <typename T, bool kNeedTheta>
 __global__ void __launch_bounds__(kTiledThreads, 3)
@@ -232,7 +232,12 @@ struct InverseLayer {
 
 static_assert(sizeof(InverseLayer) <= 128, "workspace reserves 128 B per layer plan");
 
-static __global__ void inverse_plans_kernel(const float* __restrict__ theta, InverseLayer* __restrict__ plans, int n, int H, int W) {
+// Also builds the launch order of pass 2: layers whose per-texel window is huge (strongly magnifying or
+// near-singular placements, a few hundred candidates per texel) are scheduled FIRST so that their long-running
+// blocks overlap the rest of the grid instead of forming a tail (longest-processing-time-first).
+// order[0..n): heavy layers from the front, the others from the back; cnt[2] zeroed by the caller.
+static __global__ void inverse_plans_kernel(const float* __restrict__ theta, InverseLayer* __restrict__ plans, int n, int H, int W,
+                                            int* __restrict__ order, int* __restrict__ cnt) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const float* th = theta + (long long)k * 6;
@@ -251,6 +256,9 @@ static __global__ void inverse_plans_kernel(const float* __restrict__ theta, Inv
   q.r00 = fabs(a00) > 1e-6 ? (float)(1.0 / a00) : 0.f;
   q.r10 = fabs(a10) > 1e-6 ? (float)(1.0 / a10) : 0.f;
   q.wide = (2.0 * rj > 3.5) || (2.0 * ri > 3.5);
+  const bool heavy = q.valid && fmin(rj, (double)W) * fmin(ri, (double)H) > 64.0;
+  if (heavy) order[atomicAdd(&cnt[0], 1)] = k;
+  else order[n - 1 - atomicAdd(&cnt[1], 1)] = k;
   // what STNv2c emits (convert_translate_to_2x3, image_utils.py:316-335): the adjoint is a fixed 2x2 stencil
   q.shift_only = is_pure_shift(th);
   const double fX = floor(q.c0), fY = floor(q.c1);
@@ -293,12 +301,12 @@ template <> struct Pack2<__half> {
 __device__ __forceinline__ float hat(float u) { return fmaxf(1.f - fabsf(u), 0.f); }
 
 template <typename T>
-__global__ void __launch_bounds__(256)
-render_bwd_pass2(const InverseLayer* __restrict__ plans, const float2* __restrict__ rec, const float4* __restrict__ gp,
-                 T* __restrict__ gx, Geometry g, int skip_shift) {
+__global__ void __launch_bounds__(256, 4)
+render_bwd_pass2(const InverseLayer* __restrict__ plans, const int* __restrict__ order, const float2* __restrict__ rec,
+                 const float4* __restrict__ gp, T* __restrict__ gx, Geometry g, int skip_shift) {
   __shared__ float s_jcf, s_icf;
   __shared__ int s_JC, s_IC, s_ok;
-  const int n = blockIdx.z;                     // b * L + l
+  const int n = order[blockIdx.z];              // b * L + l, heavy layers first
   const int b = n / g.L;
   const int x0b = blockIdx.x * kP2W, y0b = blockIdx.y * kP2H;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -361,49 +369,75 @@ render_bwd_pass2(const InverseLayer* __restrict__ plans, const float2* __restric
     // half extents of the pre-image of the 2 x 2 block's support: a texel's (-1,1)^2 grown by +-0.5
     const float rj = L_.rj + 0.5f * (fabsf(i00) + fabsf(i01)), ri = L_.ri + 0.5f * (fabsf(i10) + fabsf(i11));
     const int wide = L_.wide;
+    const float r00 = L_.r00, r10 = L_.r10;
     __syncthreads();
-    if (x >= g.W || y >= g.H) return;
-    if (s_ok) {
-      const int JC = s_JC, IC = s_IC;
-      const float jcf = s_jcf, icf = s_icf;
-      // centre of this thread's 2 x 2 block relative to the CTA centre, and its pre-image relative to (JC, IC)
-      const float dxl = (float)(2 * tx) + 0.5f - 0.5f * kP2W, dyl = (float)(2 * ty) + 0.5f - 0.5f * kP2H;
-      const float pj = jcf + i00 * dxl + i01 * dyl, pi = icf + i10 * dxl + i11 * dyl;
-      const float mlo = fmaxf(ceilf(pj - rj), (float)(-JC)), mhi = fminf(floorf(pj + rj), (float)(g.W - 1 - JC));
-      const float nlo = fmaxf(ceilf(pi - ri), (float)(-IC)), nhi = fminf(floorf(pi + ri), (float)(g.H - 1 - IC));
-      if (mlo <= mhi && nlo <= nhi) {
-        const int m0 = (int)mlo, m1 = (int)mhi, n0 = (int)nlo, n1 = (int)nhi;
-        const float x0l = dxl - 0.5f, y0l = dyl - 0.5f;          // texel (0,0) of the block relative to the CTA centre
-        float di = nlo - icf;
-        const float2* recn = rec + (long long)n * hw + ((IC + n0) * g.W + JC);
-        const float4* gpb = gp + (long long)b * hw + ((IC + n0) * g.W + JC);
-        const float dj0 = mlo - jcf;
-        for (int nn = n0; nn <= n1; ++nn, di += 1.f, recn += g.W, gpb += g.W) {
-          const float ub = fmaf(a01, di, -x0l), vb = fmaf(a11, di, -y0l);
-          int ma = m0, mb = m1;
-          float dja = dj0;
-          if (wide) {
-            // magnifying or near-singular placement: solve |a00 dj + ub - kx| < 1, |a10 dj + vb - ky| < 1 for the
-            // row (dj = mm - jcf; kx, ky in {0, 1}) and keep one candidate of slack on either side
-            float lo = -3.0e9f, hi = 3.0e9f;
-            if (L_.r00 != 0.f) {
-              const float t0 = (-1.f - ub) * L_.r00, t1 = (2.f - ub) * L_.r00;
-              lo = fmaxf(lo, fminf(t0, t1)); hi = fminf(hi, fmaxf(t0, t1));
-            } else if (ub <= -1.f || ub >= 2.f) { hi = -3.0e9f; }
-            if (L_.r10 != 0.f) {
-              const float t0 = (-1.f - vb) * L_.r10, t1 = (2.f - vb) * L_.r10;
-              lo = fmaxf(lo, fminf(t0, t1)); hi = fminf(hi, fmaxf(t0, t1));
-            } else if (vb <= -1.f || vb >= 2.f) { hi = -3.0e9f; }
-            lo = fmaxf(floorf(lo + jcf) - 1.f, mlo);
-            hi = fminf(ceilf(hi + jcf) + 1.f, mhi);
-            if (!(lo <= hi)) continue;
-            ma = (int)lo; mb = (int)hi;
-            dja = lo - jcf;
-          }
-          float u = fmaf(a00, dja, ub);                          // ix(candidate) - x of texel column 0
-          float v = fmaf(a10, dja, vb);                          // iy(candidate) - y of texel row 0
+    const int JC = s_JC, IC = s_IC;
+    const float jcf = s_jcf, icf = s_icf;
+    // centre of this thread's 2 x 2 block relative to the CTA centre, and its pre-image relative to (JC, IC)
+    const float dxl = (float)(2 * tx) + 0.5f - 0.5f * kP2W, dyl = (float)(2 * ty) + 0.5f - 0.5f * kP2H;
+    const float pj = jcf + i00 * dxl + i01 * dyl, pi = icf + i10 * dxl + i11 * dyl;
+    float mlo = fmaxf(ceilf(pj - rj), (float)(-JC)), mhi = fminf(floorf(pj + rj), (float)(g.W - 1 - JC));
+    float nlo = fmaxf(ceilf(pi - ri), (float)(-IC)), nhi = fminf(floorf(pi + ri), (float)(g.H - 1 - IC));
+    const bool has = s_ok && x < g.W && y < g.H && mlo <= mhi && nlo <= nhi;
+    if (!has) { mlo = 0.f; mhi = -1.f; nlo = 0.f; nhi = -1.f; }
+    float x0l = dxl - 0.5f, y0l = dyl - 0.5f;                  // texel (0,0) of the block relative to the CTA centre
+    const float2* rec0 = rec + (long long)n * hw + (IC * g.W + JC);
+    const float4* gp0 = gp + (long long)b * hw + (IC * g.W + JC);
+
+    // one candidate row nn of the window (mlo_..mhi_) of the block at (x0l_, y0l_), accumulated into acc_
+    auto row = [&](int nn, float mlo_, float mhi_, float x0l_, float y0l_, f32x2 (&acc_)[2][2][2]) {
+      const float di = (float)nn - icf;
+      const float ub = fmaf(a01, di, -x0l_), vb = fmaf(a11, di, -y0l_);
+      float lo = mlo_, hi = mhi_;
+      {
+        // magnifying or near-singular placement: solve |a00 dj + ub - kx| < 1, |a10 dj + vb - ky| < 1 for the row
+        // (dj = mm - jcf; kx, ky in {0, 1}) and keep one candidate of slack on either side (its weight is 0)
+        float l2 = -3.0e9f, h2 = 3.0e9f;
+        if (r00 != 0.f) {
+          const float t0 = (-1.f - ub) * r00, t1 = (2.f - ub) * r00;
+          l2 = fmaxf(l2, fminf(t0, t1)); h2 = fminf(h2, fmaxf(t0, t1));
+        } else if (ub <= -1.f || ub >= 2.f) { h2 = -3.0e9f; }
+        if (r10 != 0.f) {
+          const float t0 = (-1.f - vb) * r10, t1 = (2.f - vb) * r10;
+          l2 = fmaxf(l2, fminf(t0, t1)); h2 = fminf(h2, fmaxf(t0, t1));
+        } else if (vb <= -1.f || vb >= 2.f) { h2 = -3.0e9f; }
+        lo = fmaxf(floorf(l2 + jcf) - 1.f, mlo_);
+        hi = fminf(ceilf(h2 + jcf) + 1.f, mhi_);
+        if (!(lo <= hi)) return;
+      }
+      const int ma = (int)lo, mb = (int)hi;
+      const float dja = lo - jcf;
+      float u = fmaf(a00, dja, ub);                            // ix(candidate) - x of texel column 0
+      float v = fmaf(a10, dja, vb);                            // iy(candidate) - y of texel row 0
+      const float2* recn = rec0 + nn * g.W;
+      const float4* gpb = gp0 + nn * g.W;
 #pragma unroll 1
-          for (int mm = ma; mm <= mb; ++mm, u += a00, v += a10) {
+      for (int mm = ma; mm <= mb; ++mm, u += a00, v += a10) {
+        const float wx0 = hat(u), wx1 = hat(u - 1.f), wy0 = hat(v), wy1 = hat(v - 1.f);
+        const float2 r = __ldg(recn + mm);
+        const float4 G = __ldg(gpb + mm);
+        const f32x2 grg = pk(G.x * r.x, G.y * r.x), gba = pk(G.z * r.x, r.y);
+        const f32x2 w00 = bc(wy0 * wx0), w01 = bc(wy0 * wx1), w10 = bc(wy1 * wx0), w11 = bc(wy1 * wx1);
+        acc_[0][0][0] = fma2(w00, grg, acc_[0][0][0]); acc_[0][0][1] = fma2(w00, gba, acc_[0][0][1]);
+        acc_[0][1][0] = fma2(w01, grg, acc_[0][1][0]); acc_[0][1][1] = fma2(w01, gba, acc_[0][1][1]);
+        acc_[1][0][0] = fma2(w10, grg, acc_[1][0][0]); acc_[1][0][1] = fma2(w10, gba, acc_[1][0][1]);
+        acc_[1][1][0] = fma2(w11, grg, acc_[1][1][0]); acc_[1][1][1] = fma2(w11, gba, acc_[1][1][1]);
+      }
+    };
+
+    if (!wide) {
+      // the common case (|det| ~ 1): a 3..5 x 3..5 candidate window, plain serial loops, no refinement
+      if (has) {
+        const int m0 = (int)mlo, m1 = (int)mhi, n0 = (int)nlo, n1 = (int)nhi;
+        const float dj0 = mlo - jcf;
+        float di = nlo - icf;
+        const float2* recn = rec0 + n0 * g.W;
+        const float4* gpb = gp0 + n0 * g.W;
+        for (int nn = n0; nn <= n1; ++nn, di += 1.f, recn += g.W, gpb += g.W) {
+          float u = fmaf(a00, dj0, fmaf(a01, di, -x0l));
+          float v = fmaf(a10, dj0, fmaf(a11, di, -y0l));
+#pragma unroll 1
+          for (int mm = m0; mm <= m1; ++mm, u += a00, v += a10) {
             const float wx0 = hat(u), wx1 = hat(u - 1.f), wy0 = hat(v), wy1 = hat(v - 1.f);
             const float2 r = __ldg(recn + mm);
             const float4 G = __ldg(gpb + mm);
@@ -416,7 +450,41 @@ render_bwd_pass2(const InverseLayer* __restrict__ plans, const float2* __restric
           }
         }
       }
+    } else {
+      // Windows with many rows (near-singular / strongly magnifying placements) occur on a handful of lanes
+      // per warp; left alone they serialise hundreds of dependent row iterations on those lanes.  The warp
+      // takes them one at a time instead: 32 lanes share the rows of ONE block, then a butterfly adds the partials.
+      const int lane = threadIdx.x & 31;
+      const bool heavy = has && (nhi - nlo >= 31.f);
+      unsigned todo = __ballot_sync(0xffffffffu, heavy);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const float mlo_s = __shfl_sync(0xffffffffu, mlo, src), mhi_s = __shfl_sync(0xffffffffu, mhi, src);
+        const int n0_s = (int)__shfl_sync(0xffffffffu, nlo, src), n1_s = (int)__shfl_sync(0xffffffffu, nhi, src);
+        const float x0l_s = __shfl_sync(0xffffffffu, x0l, src), y0l_s = __shfl_sync(0xffffffffu, y0l, src);
+        f32x2 part[2][2][2];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) (&part[0][0][0])[q] = 0ull;
+        for (int nn = n0_s + lane; nn <= n1_s; nn += 32) row(nn, mlo_s, mhi_s, x0l_s, y0l_s, part);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float p0, p1;
+          upk((&part[0][0][0])[q], p0, p1);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+            p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+          }
+          if (lane == src) (&acc[0][0][0])[q] = pk(p0, p1);
+        }
+      }
+      if (has && !heavy) {
+        const int n0 = (int)nlo, n1 = (int)nhi;
+        for (int nn = n0; nn <= n1; ++nn) row(nn, mlo, mhi, x0l, y0l, acc);
+      }
     }
+    if (x >= g.W || y >= g.H) return;
   }
 #pragma unroll
   for (int ky = 0; ky < 2; ++ky) {

@@ -1,24 +1,27 @@
-import sys; sys.path.insert(0,'/root/repo')
+import sys, ctypes; sys.path.insert(0,'/root/repo')
 import torch, numpy as np
 import montage_gan_b200
-from montage_gan_b200 import render as mr, synth, _lib
-from oracle import restatement as R
-th=synth.make_theta(1,32,"I",seed=5)[:,23:26].contiguous()
-H=W=16
-x=synth.make_layers(1,3,H,W,"W",seed=5)
-xn=x.numpy(); thn=th.numpy()
-t=thn[0,1]
-bad=[]
-for i in range(8,16):
-  for j in range(8,16):
-    g2=torch.zeros(1,4,H,W); g2[0,:,i,j]=torch.tensor([1.,-2.,0.5,1.5])
-    r=R.render_fwd_bwd(xn,thn,g2.numpy(),"m11",np.float64)
-    xx=x.cuda().requires_grad_(True); tt=th.cuda().requires_grad_(True)
-    o=mr.render(xx,tt); o.backward(g2.cuda()); torch.cuda.synchronize()
-    gt=tt.grad.cpu().numpy().reshape(3,6)[1]; rf=r['grad_theta'].reshape(3,6)[1]
-    e=np.abs(gt-rf).max()/max(1e-9,np.abs(rf).max())
-    if e>1e-4:
-        ix=t[0,0]*(j+.5-8)+t[0,1]*(i+.5-8)+t[0,2]*8+7.5; iy=t[1,0]*(j+.5-8)+t[1,1]*(i+.5-8)+t[1,2]*8+7.5
-        bad.append((i,j,round(float(ix),3),round(float(iy),3),gt[3:].round(4).tolist(),rf[3:].round(4).tolist()))
-print(len(bad)); 
-for b in bad[:12]: print(b)
+from montage_gan_b200 import synth, _lib
+lib=_lib.load(); dev=torch.device('cuda',0)
+B,L,H,W=64,7,256,256; dt=1
+P=lambda t: ctypes.c_void_p(t.data_ptr())
+x=synth.make_layers(8,L,H,W,"S",seed=0).repeat(8,1,1,1,1).to(dev,torch.bfloat16).contiguous()
+go=synth.make_grad_out(B,H,W,seed=0).to(dev,torch.bfloat16)
+out=torch.empty(B,4,H,W,dtype=torch.bfloat16,device=dev); gx=torch.empty_like(x); gt=torch.empty(B,L,2,3,device=dev)
+sav=torch.empty(lib.mgr_saved_alpha_bytes(B,L,H,W,dt),dtype=torch.uint8,device=dev)
+wsb=lib.mgr_render_backward_workspace_bytes(B,L,H,W,dt,1,3); ws=torch.empty(wsb,dtype=torch.uint8,device=dev)
+sp=ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+for seed in range(6):
+    thc=synth.make_theta(B,L,"I",seed=seed); th=thc.to(dev)
+    det=(thc[...,0,0]*thc[...,1,1]-thc[...,0,1]*thc[...,1,0]).abs().flatten()
+    def f(): lib.mgr_render_forward(P(x),None,P(th),P(out),P(sav),B,L,H,W,dt,0,sp)
+    def b(): lib.mgr_render_backward(P(x),None,P(th),P(out),P(go),P(sav),P(gx),P(gt),P(ws),wsb,B,L,H,W,dt,0,3,sp)
+    f(); b(); torch.cuda.synchronize()
+    res={}
+    for name,fn in (('fwd',f),('bwd',b)):
+        e0,e1=torch.cuda.Event(enable_timing=True),torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5): fn()
+        e1.record(); torch.cuda.synchronize(); res[name]=e0.elapsed_time(e1)/5*1e3
+    srt=np.sort(det.numpy())
+    print(seed, {k:round(v) for k,v in res.items()}, 'smallest |det|', np.round(srt[:5],3), 'n<0.2:', int((srt<0.2).sum()))
