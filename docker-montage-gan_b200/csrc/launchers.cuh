@@ -97,24 +97,26 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
     float4* gp = reinterpret_cast<float4*>(reinterpret_cast<char*>(ws) + sizeof(float2) * (size_t)g.B * g.L * g.H * g.W);
     InverseLayer* inv = reinterpret_cast<InverseLayer*>(reinterpret_cast<char*>(gp) + sizeof(float4) * (size_t)g.B * g.H * g.W);
     int* order = reinterpret_cast<int*>(inv + (size_t)g.B * g.L);          // [B*L] + 2 counters
-    static bool configured = false;
-    if (!configured) {
-      MGR_CUDA(cudaFuncSetAttribute(render_bwd_pass1<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      MGR_CUDA(cudaFuncSetAttribute(render_bwd_pass1<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
-    }
     if (nt) MGR_CUDA(cudaMemsetAsync(gtheta, 0, sizeof(float) * 6 * g.B * g.L, s));
-    const size_t smem = tiled_smem_bytes(g.L, sizeof(Vec)) + sizeof(float) * ((6 * g.L + 3) & ~3) +
-                        sizeof(float) * (size_t)g.L * kPx * kTiledThreads +         // + transmittance stash
-                        sizeof(float4) * kPx * kTiledThreads;                       // + (G_P, G_A) per pixel
+    size_t smem = tiled_smem_bytes(g.L, sizeof(Vec)) + sizeof(float) * ((6 * g.L + 3) & ~3) +
+                  sizeof(float) * (size_t)g.L * kPx * kTiledThreads;                // + transmittance stash
+    const size_t gp_bytes = sizeof(float4) * kPx * kTiledThreads;                   // (G_P, G_A) copy, if 3 CTAs/SM still fit
+    const bool gp_smem = (smem + gp_bytes) * 3 + 3 * 1024 <= 227 * 1024;
+    if (gp_smem) smem += gp_bytes;
     dim3 grid((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B);
     const int shift = debug_path() != 2;
-    if (nt)
-      render_bwd_pass1<T, true><<<grid, kTiledThreads, smem, s>>>((const T*)x, theta, (const T*)out, (const T*)gout,
-                                                                  (const SA*)sav, rec, gp, gtheta, g, shift);
-    else
-      render_bwd_pass1<T, false><<<grid, kTiledThreads, smem, s>>>((const T*)x, theta, (const T*)out, (const T*)gout,
-                                                                   (const SA*)sav, rec, gp, nullptr, g, shift);
+    {
+      auto launch = [&](auto kern) -> int {
+        MGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        kern<<<grid, kTiledThreads, smem, s>>>((const T*)x, theta, (const T*)out, (const T*)gout, (const SA*)sav, rec, gp,
+                                               nt ? gtheta : nullptr, g, shift);
+        return MGR_OK;
+      };
+      int rc;
+      if (nt) rc = gp_smem ? launch(render_bwd_pass1<T, true, true>) : launch(render_bwd_pass1<T, true, false>);
+      else rc = gp_smem ? launch(render_bwd_pass1<T, false, true>) : launch(render_bwd_pass1<T, false, false>);
+      if (rc) return rc;
+    }
     MGR_CUDA(cudaGetLastError());
     count_launch();
     if (nx) {
@@ -129,24 +131,21 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
       count_launch();
     }
     if (shift) {
-      static bool configured2 = false;
-      if (!configured2) {
-        MGR_CUDA(cudaFuncSetAttribute(render_bwd_shift<T, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        MGR_CUDA(cudaFuncSetAttribute(render_bwd_shift<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        MGR_CUDA(cudaFuncSetAttribute(render_bwd_shift<T, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured2 = true;
-      }
-      const size_t smem3 = shift_bwd_smem_bytes(g.L, sizeof(Vec));
+      size_t smem3 = shift_bwd_smem_bytes(g.L, sizeof(Vec));
+      const bool gp_smem3 = (smem3 + gp_bytes) * 3 + 3 * 1024 <= 227 * 1024;
+      if (gp_smem3) smem3 += gp_bytes;
       dim3 grid3((g.W + 1 + kAnchor - 1) / kAnchor, (g.H + 1 + kAnchor - 1) / kAnchor, g.B);
-      if (nx && nt)
-        render_bwd_shift<T, true, true><<<grid3, kTiledThreads, smem3, s>>>((const T*)x, theta, (const T*)out, (const T*)gout,
-                                                                            (const SA*)sav, (T*)gx, gtheta, g);
-      else if (nx)
-        render_bwd_shift<T, true, false><<<grid3, kTiledThreads, smem3, s>>>((const T*)x, theta, (const T*)out, (const T*)gout,
-                                                                             (const SA*)sav, (T*)gx, nullptr, g);
-      else
-        render_bwd_shift<T, false, true><<<grid3, kTiledThreads, smem3, s>>>((const T*)x, theta, (const T*)out, (const T*)gout,
-                                                                             (const SA*)sav, nullptr, gtheta, g);
+      auto launch3 = [&](auto kern) -> int {
+        MGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        kern<<<grid3, kTiledThreads, smem3, s>>>((const T*)x, theta, (const T*)out, (const T*)gout, (const SA*)sav,
+                                                 nx ? (T*)gx : nullptr, nt ? gtheta : nullptr, gp, g);
+        return MGR_OK;
+      };
+      int rc;
+      if (nx && nt) rc = gp_smem3 ? launch3(render_bwd_shift<T, true, true, true>) : launch3(render_bwd_shift<T, true, true, false>);
+      else if (nx) rc = gp_smem3 ? launch3(render_bwd_shift<T, true, false, true>) : launch3(render_bwd_shift<T, true, false, false>);
+      else rc = gp_smem3 ? launch3(render_bwd_shift<T, false, true, true>) : launch3(render_bwd_shift<T, false, true, false>);
+      if (rc) return rc;
       MGR_CUDA(cudaGetLastError());
       count_launch();
     }

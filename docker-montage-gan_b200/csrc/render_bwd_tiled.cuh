@@ -26,11 +26,11 @@
 namespace mgr {
 
 // workspace layout of the tiled backward (all fp32):
-//   rec [B*L][H*W] float2 = (T_l a_l, d a_l)        gp [B][H*W] float4 = (G_P.rgb, unused)
+//   rec [B*L][H*W] float2 = (T_l a_l, d a_l)        gp [B][H*W] float4 = (G_P.rgb, G_A)
 //   inverse plans [B*L] InverseLayer (128 B each)        order [B*L] int + 2 counters
 
-template <typename T, bool kNeedTheta>
-__global__ void __launch_bounds__(kTiledThreads, 3)
+template <typename T, bool kNeedTheta, bool kGPSmem>
+__global__ void __launch_bounds__(kTiledThreads, kGPSmem ? 3 : 2)
 render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const T* __restrict__ out,
                  const T* __restrict__ gout, const typename SavedAlpha<T>::type* __restrict__ sav,
                  float2* __restrict__ rec, float4* __restrict__ gp, float* __restrict__ gtheta, Geometry g,
@@ -43,7 +43,9 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
   const int tid = threadIdx.x;
   const int gth_pad = (6 * g.L + 3) & ~3;                   // keep the arrays behind it 16-byte aligned
   float* Tst = gth_acc + gth_pad + tid;                     // [L][kPx][256]: transmittance in front of layer l
-  float4* GPs = reinterpret_cast<float4*>(gth_acc + gth_pad + (size_t)g.L * kPx * kTiledThreads) + tid;   // [kPx][256]: (G_P, G_A)
+  // (G_P, G_A) per pixel: a shared-memory copy when it still leaves room for 3 CTAs/SM (host decides), else the
+  // thread re-reads its own entries of the global gp buffer (L1/L2 hits)
+  float4* GPs = reinterpret_cast<float4*>(gth_acc + gth_pad + (size_t)g.L * kPx * kTiledThreads) + tid;   // [kPx][256]
   const int b = blockIdx.z;
   if (skip_shift && cta_all_shift(theta + (long long)b * g.L * 6, g.L, tid, kTiledThreads)) return;   // render_bwd_shift's
   const int j0 = blockIdx.x * kTW, i0 = blockIdx.y * kTH;
@@ -67,6 +69,7 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
   float2* recb = rec + (long long)b * g.L * hw + pix0;
   const typename SavedAlpha<T>::type* savb = sav + (long long)b * g.L * hw + pix0;
 
+  float4* gpp = gp + (long long)b * hw + pix0;                 // (G_P, G_A) of this thread's pixels: gpp[k * row8]
   // ---- pre-pass: T_l (stashed in shared memory) and A ------------------------------------------------
   {
     float GP0[kPx], GP1[kPx], GP2[kPx], GA[kPx];
@@ -102,9 +105,9 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
           GP0[k] = g0 * inv; GP1[k] = g1 * inv; GP2[k] = g2 * inv;
           GA[k] = g3 - (g0 * o0 + g1 * o1 + g2 * o2) * inv;
         }
-        gp[(long long)b * hw + pix0 + k * row8] = make_float4(GP0[k], GP1[k], GP2[k], 0.f);
+        gpp[k * row8] = make_float4(GP0[k], GP1[k], GP2[k], GA[k]);      // pass 2 reads it (and this thread, see above)
       }
-      GPs[k * kTiledThreads] = make_float4(GP0[k], GP1[k], GP2[k], GA[k]);
+      if (kGPSmem) GPs[k * kTiledThreads] = make_float4(GP0[k], GP1[k], GP2[k], GA[k]);
     }
   }
 
@@ -126,7 +129,7 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
         if (live[k]) {
           const float T_l = Tst[(l * kPx + k) * kTiledThreads];
           // c_l = 0 in the compositing domain (transparent black)
-          const float4 G4 = GPs[k * kTiledThreads];
+          const float4 G4 = kGPSmem ? GPs[k * kTiledThreads] : gpp[k * row8];
           const float ga = T_l * (-(G4.x * S0[k] + G4.y * S1[k] + G4.z * S2[k]) + G4.w * (1.f - R[k]));
           rl[k * row8] = make_float2(0.f, ga);
         }
@@ -179,7 +182,7 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
       }
       const float T_l = Tst[(l * kPx + k) * kTiledThreads];
       const float ta = T_l * a;
-      const float4 G4 = GPs[k * kTiledThreads];
+      const float4 G4 = kGPSmem ? GPs[k * kTiledThreads] : (live[k] ? gpp[k * row8] : make_float4(0.f, 0.f, 0.f, 0.f));
       const float ga = T_l * (G4.x * (r_ - S0[k]) + G4.y * (g_ - S1[k]) + G4.z * (b_ - S2[k]) + G4.w * (1.f - R[k]));
       if (live[k]) rl[k * row8] = make_float2(ta, ga);
       if (kNeedTheta) {

@@ -151,11 +151,11 @@ inline size_t shift_fwd_smem_bytes(int L, size_t vec_bytes) { return vec_bytes *
 // ---------------------------------------------------------------------------------------------
 constexpr int kAnchor = kTW - 1;
 
-template <typename T, bool kNeedX, bool kNeedTheta>
-__global__ void __launch_bounds__(kTiledThreads, 3)
+template <typename T, bool kNeedX, bool kNeedTheta, bool kGPSmem>
+__global__ void __launch_bounds__(kTiledThreads, kGPSmem ? 3 : 2)
 render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const T* __restrict__ out,
                  const T* __restrict__ gout, const typename SavedAlpha<T>::type* __restrict__ sav,
-                 T* __restrict__ gx, float* __restrict__ gtheta, Geometry g) {
+                 T* __restrict__ gx, float* __restrict__ gtheta, float4* __restrict__ gp, Geometry g) {
   using Vec = typename Texel<T>::Vec;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Vec* buf = reinterpret_cast<Vec*>(smem_raw);                                           // [kShiftCap]
@@ -165,7 +165,6 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
   const int tid = threadIdx.x;
   const int gth_pad = (6 * g.L + 3) & ~3;
   float* Tst = gth_acc + gth_pad + tid;                                                  // [L][kPx][256]
-  float4* GPs = reinterpret_cast<float4*>(gth_acc + gth_pad + (size_t)g.L * kPx * kTiledThreads) + tid;   // [kPx][256]
   const int b = blockIdx.z;
   const float* thb = theta + (long long)b * g.L * 6;
   if (!cta_all_shift(thb, g.L, tid, kTiledThreads)) return;
@@ -193,6 +192,10 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
     own[k] = live[k] && tx >= 1 && (kPx * ty + k) >= 1;
   }
   const typename SavedAlpha<T>::type* savb = sav + (long long)b * g.L * hw + pix0;
+  // (G_P, G_A) per pixel lives in the workspace (re-read per layer: L1/L2 hits).  Halo pixels are written by
+  // two or four overlapping tiles with identical values.
+  float4* gpp = gp + (long long)b * hw + pix0;
+  float4* GPs = reinterpret_cast<float4*>(gth_acc + gth_pad + (size_t)g.L * kPx * kTiledThreads) + tid;   // [kPx][256], if it fits
 
   // ---- pre-pass: T_l and A from the saved alpha samples ---------------------------------------------
   {
@@ -228,7 +231,8 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
           GA[k] = g3 - (g0 * o0 + g1 * o1 + g2 * o2) * inv;
         }
       }
-      GPs[k * kTiledThreads] = make_float4(GP0[k], GP1[k], GP2[k], GA[k]);
+      if (kGPSmem) GPs[k * kTiledThreads] = make_float4(GP0[k], GP1[k], GP2[k], GA[k]);
+      else if (live[k]) gpp[k * g.W] = make_float4(GP0[k], GP1[k], GP2[k], GA[k]);
     }
   }
 
@@ -293,7 +297,7 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
         h_rg = n_rg; h_ba = n_ba; d_rg = e_rg; d_ba = e_ba;
         const float T_l = Tst[(l * kPx + k) * kTiledThreads];
         const float ta = T_l * a;
-        const float4 G4 = GPs[k * kTiledThreads];
+        const float4 G4 = kGPSmem ? GPs[k * kTiledThreads] : (live[k] ? gpp[k * g.W] : make_float4(0.f, 0.f, 0.f, 0.f));
         const float ga = T_l * (G4.x * (r_ - S0[k]) + G4.y * (g_ - S1[k]) + G4.z * (b_ - S2[k]) + G4.w * (1.f - R[k]));
         const float gr = G4.x * ta, gg = G4.y * ta, gb = G4.z * ta;
         if (kNeedX) Gt[k * kTW] = make_float4(gr, gg, gb, ga);
@@ -374,7 +378,7 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
 
 inline size_t shift_bwd_smem_bytes(int L, size_t vec_bytes) {
   return vec_bytes * kShiftCap + sizeof(float4) * kTW * kTH + sizeof(ShiftPlan) * L + sizeof(float) * ((6 * L + 3) & ~3) +
-         sizeof(float) * (size_t)L * kPx * kTiledThreads + sizeof(float4) * kPx * kTiledThreads;
+         sizeof(float) * (size_t)L * kPx * kTiledThreads;
 }
 
 }  // namespace mgr
