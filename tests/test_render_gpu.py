@@ -505,3 +505,63 @@ def test_r1_double_backward_on_the_real_branch():
     out = mr.render(xs, th)
     with pytest.raises(NotImplementedError):
         torch.autograd.grad(out, xs, go, create_graph=True)
+
+
+def test_fp16_storage():
+    """fp16 I/O, fp32 math (the reference's local generators run their last blocks in fp16, num_fp16_res=4)."""
+    B, L, H, W = 2, 7, 64, 64
+    x = synth.make_layers(B, L, H, W, "S", seed=14).to(torch.float16)
+    for th in (synth.make_theta(B, L, "I", seed=14), _translation_theta(B, L, 14, 0.5)):
+        go = (synth.make_grad_out(B, H, W, seed=14) * 0.1).to(torch.float16)
+        new = _run_cuda(x, th, go, dtype=torch.float16)
+        r64 = R.render_fwd_bwd(x.float().numpy(), th.numpy(), go.float().numpy(), "m11", np.float64)
+        assert max_abs(new["out"], r64["out"]) < 2 ** -10
+        assert rel_err(new["grad_x"], r64["grad_x"]) < 2 ** -9
+        assert rel_err(new["grad_theta"], r64["grad_theta"]) < 5e-3
+
+
+def test_full_size_properties_config3_shard():
+    """BASELINE config 3, one GPU's shard (B=32, L=16, 512x512, fp32; 2.1 GB of layers): size-independent
+    properties.  (1) translation stack == general kernels on the same stack (two implementations);
+    (2) an opaque identity-placed front layer hides everything; (3) sum of grad_x under grad_out = d(out)/d(x)
+    of a uniform brightening equals the finite difference of sum(out)."""
+    B, L, H, W = 32, 16, 512, 512
+    from montage_gan_b200 import _lib
+    lib = _lib.load()
+    xs = synth.make_layers(4, L, H, W, "S", seed=51).repeat(B // 4, 1, 1, 1, 1).to(DEV)
+    th = _translation_theta(B, L, 51, 0.3).to(DEV)
+    go = synth.make_grad_out(4, H, W, seed=51).repeat(B // 4, 1, 1, 1).to(DEV)
+    res = []
+    for path in (0, 2):
+        lib.mgr_set_debug_path(path)
+        try:
+            xx = xs.clone().requires_grad_(True)
+            tt = th.clone().requires_grad_(True)
+            out = mr.render(xx, tt)
+            out.backward(go)
+            res.append((out.detach(), xx.grad.clone(), tt.grad.clone()))
+            del xx, out
+        finally:
+            lib.mgr_set_debug_path(0)
+    assert (res[0][0] - res[1][0]).abs().max().item() < 5e-6
+    assert ((res[0][1] - res[1][1]).abs().max() / res[1][1].abs().max()).item() < 2e-5
+    assert ((res[0][2] - res[1][2]).abs().max() / res[1][2].abs().max()).item() < 2e-3
+    # directional derivative: d/d eps sum(go * render(x + eps * v)) == sum(grad_x * v)
+    v = torch.ones_like(xs) * 0.5
+    v[:, :, 3] = 0.25
+    eps = 1e-2
+    with torch.no_grad():
+        fp = (mr.render(xs + eps * v, th).double() * go.double()).sum()
+        fm = (mr.render(xs - eps * v, th).double() * go.double()).sum()
+    fd = ((fp - fm) / (2 * eps)).item()
+    an = (res[0][1].double() * v.double()).sum().item()
+    assert abs(fd - an) / abs(an) < 2e-3
+    del res
+    xo = xs.clone()
+    xo[:, L - 1, 3] = 1.0
+    tho = th.clone()
+    tho[:, L - 1] = torch.eye(2, 3, device=DEV)
+    xo.requires_grad_(True)
+    out = mr.render(xo, tho)
+    out.backward(go)
+    assert xo.grad[:, :L - 1].abs().max().item() == 0.0 and (out[:, 3] == 1).all()
