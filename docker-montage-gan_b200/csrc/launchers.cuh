@@ -98,7 +98,7 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
     InverseLayer* inv = reinterpret_cast<InverseLayer*>(reinterpret_cast<char*>(gp) + sizeof(float4) * (size_t)g.B * g.H * g.W);
     int* order = reinterpret_cast<int*>(inv + (size_t)g.B * g.L);          // [B*L] + 2 counters
     if (nt) MGR_CUDA(cudaMemsetAsync(gtheta, 0, sizeof(float) * 6 * g.B * g.L, s));
-    size_t smem = tiled_smem_bytes(g.L, sizeof(Vec)) + sizeof(float) * ((6 * g.L + 3) & ~3) +
+    size_t smem = align16(tiled_smem_bytes(g.L, sizeof(Vec))) +
                   sizeof(float) * (size_t)g.L * kPx * kTiledThreads;                // + transmittance stash
     const size_t gp_bytes = sizeof(float4) * kPx * kTiledThreads;                   // (G_P, G_A) copy, if 3 CTAs/SM still fit
     const bool gp_smem = (smem + gp_bytes) * 3 + 3 * 1024 <= 227 * 1024;

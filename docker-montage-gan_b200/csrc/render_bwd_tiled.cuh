@@ -39,21 +39,19 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Vec* buf = reinterpret_cast<Vec*>(smem_raw);                                            // [kCapTexels]
   LayerPlan* plan = reinterpret_cast<LayerPlan*>(smem_raw + sizeof(Vec) * kCapTexels);    // [L]
-  float* gth_acc = reinterpret_cast<float*>(plan + g.L);                                  // [L][6]
   const int tid = threadIdx.x;
-  const int gth_pad = (6 * g.L + 3) & ~3;                   // keep the arrays behind it 16-byte aligned
-  float* Tst = gth_acc + gth_pad + tid;                     // [L][kPx][256]: transmittance in front of layer l
+  // [L][kPx][256]: transmittance in front of layer l, later the layer's theta-gradient partials (16-byte aligned)
+  float* stash = reinterpret_cast<float*>(smem_raw + align16(sizeof(Vec) * kCapTexels + sizeof(LayerPlan) * g.L));
+  float* Tst = stash + tid;
   // (G_P, G_A) per pixel: a shared-memory copy when it still leaves room for 3 CTAs/SM (host decides), else the
   // thread re-reads its own entries of the global gp buffer (L1/L2 hits)
-  float4* GPs = reinterpret_cast<float4*>(gth_acc + gth_pad + (size_t)g.L * kPx * kTiledThreads) + tid;   // [kPx][256]
+  float4* GPs = reinterpret_cast<float4*>(stash + (size_t)g.L * kPx * kTiledThreads) + tid;   // [kPx][256]
   const int b = blockIdx.z;
   if (skip_shift && cta_all_shift(theta + (long long)b * g.L * 6, g.L, tid, kTiledThreads)) return;   // render_bwd_shift's
   const int j0 = blockIdx.x * kTW, i0 = blockIdx.y * kTH;
   const int tx = tid & 31, ty = tid >> 5;
   for (int l = tid; l < g.L; l += kTiledThreads)
     plan[l] = plan_layer(theta + ((long long)b * g.L + l) * 6, g.H, g.W, j0, i0, kStageVec);
-  if (kNeedTheta)
-    for (int k = tid; k < g.L * 6; k += kTiledThreads) gth_acc[k] = 0.f;
   __syncthreads();
 
   const float zs = g.m11 ? 0.5f : 1.f;
@@ -76,16 +74,23 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
     float Tc[kPx], A[kPx];
 #pragma unroll
     for (int k = 0; k < kPx; ++k) { Tc[k] = 1.f; A[k] = 0.f; }
+    // running pointers (front layer first): keeps the loop free of 64-bit index arithmetic
+    const typename SavedAlpha<T>::type* sa[kPx];
+#pragma unroll
+    for (int k = 0; k < kPx; ++k) sa[k] = savb + (long long)(g.L - 1) * hw + k * row8;
+    float* tp = Tst + (g.L - 1) * kPx * kTiledThreads;
     for (int l = g.L - 1; l >= 0; --l) {
 #pragma unroll
       for (int k = 0; k < kPx; ++k) {
-        Tst[(l * kPx + k) * kTiledThreads] = live[k] ? Tc[k] : 0.f;
+        tp[k * kTiledThreads] = live[k] ? Tc[k] : 0.f;
         if (live[k]) {
-          const float a = ld_alpha(savb + (long long)l * hw + k * row8);
+          const float a = ld_alpha(sa[k]);
           A[k] = fmaf(Tc[k], a, A[k]);
           Tc[k] *= (1.f - a);
         }
+        sa[k] -= hw;
       }
+      tp -= kPx * kTiledThreads;
     }
     // upstream gradient in the compositing domain: o = P / A
     const float gs = g.m11 ? 2.f : 1.f;                       // d out / d o
@@ -134,6 +139,7 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
           rl[k * row8] = make_float2(0.f, ga);
         }
       }
+      if (kNeedTheta) park_theta_partials(Tst + l * kPx * kTiledThreads, 0.f, 0.f, 0.f, 0.f);
       continue;                              // the footprint misses the image: no texel, no theta gradient
     }
     const T* img = xb + (long long)l * g.sl;
@@ -199,17 +205,13 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
       S2[k] = fmaf(om, S2[k], a * b_);
       R[k] = fmaf(om, R[k], a);
     }
-    if (kNeedTheta) {
-      // this thread's four pixels share the column: (ggx x_j, ggx y_i, ggx, ggy x_j, ggy y_i, ggy)
-      float part[6] = {hW * accx * xj, hW * accxy, hW * accx, hH * accy * xj, hH * accyy, hH * accy};
-      const float s = warp_sum6(part, tx);
-      const int q = warp_sum6_index(tx);
-      if ((tx & 3) == 0 && q < 6) atomicAdd(&gth_acc[l * 6 + q], s);
-    }
+    // the T_l slots of this layer are dead: park the thread's theta-gradient partials there (tile_common.cuh)
+    if (kNeedTheta) park_theta_partials(Tst + l * kPx * kTiledThreads, accx, accxy, accy, accyy);
   }
   if (kNeedTheta) {
     __syncthreads();
-    for (int k = tid; k < g.L * 6; k += kTiledThreads) atomicAdd(gtheta + (long long)b * g.L * 6 + k, gth_acc[k]);
+    // a thread's four pixels share the column: (ggx x_j, ggx y_i, ggx, ggy x_j, ggy y_i, ggy)
+    reduce_theta_partials(stash, g.L, tid, xj, hW, hH, gtheta + (long long)b * g.L * 6);
   }
 }
 

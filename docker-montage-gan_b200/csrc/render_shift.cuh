@@ -23,10 +23,12 @@
 
 namespace mgr {
 
-struct ShiftPlan {
+struct ShiftPlan {     // 16 bytes: arrays behind a ShiftPlan[L] stay 16-byte aligned
   int X, Y;          // integer part of the shift (pixels)
   float fx, fy;      // fractional part, in [0, 1)
 };
+
+static_assert(sizeof(ShiftPlan) == 16, "shared-memory layout of the stencil kernels");
 
 __device__ __forceinline__ ShiftPlan make_shift_plan(const float* __restrict__ th, int H, int W) {
   const double sx = (double)th[2] * 0.5 * W, sy = (double)th[5] * 0.5 * H;
@@ -160,11 +162,10 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Vec* buf = reinterpret_cast<Vec*>(smem_raw);                                           // [kShiftCap]
   float4* G = reinterpret_cast<float4*>(smem_raw + sizeof(Vec) * kShiftCap);             // [32][32] gradient records
-  ShiftPlan* splan = reinterpret_cast<ShiftPlan*>(G + kTW * kTH);                        // [L]
-  float* gth_acc = reinterpret_cast<float*>(splan + g.L);                                // [L][6]
+  ShiftPlan* splan = reinterpret_cast<ShiftPlan*>(G + kTW * kTH);                        // [L], 16 B each
   const int tid = threadIdx.x;
-  const int gth_pad = (6 * g.L + 3) & ~3;
-  float* Tst = gth_acc + gth_pad + tid;                                                  // [L][kPx][256]
+  float* stash = reinterpret_cast<float*>(splan + g.L);       // [L][kPx][256]: T_l, later the theta-gradient partials
+  float* Tst = stash + tid;
   const int b = blockIdx.z;
   const float* thb = theta + (long long)b * g.L * 6;
   if (!cta_all_shift(thb, g.L, tid, kTiledThreads)) return;
@@ -172,8 +173,6 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
   const int j0 = blockIdx.x * kAnchor - 1, i0 = blockIdx.y * kAnchor - 1;
   const int tx = tid & 31, ty = tid >> 5;
   for (int l = tid; l < g.L; l += kTiledThreads) splan[l] = make_shift_plan(thb + 6 * l, g.H, g.W);
-  if (kNeedTheta)
-    for (int k = tid; k < g.L * 6; k += kTiledThreads) gth_acc[k] = 0.f;
   __syncthreads();
 
   const float zs = g.m11 ? 0.5f : 1.f;
@@ -195,7 +194,7 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
   // (G_P, G_A) per pixel lives in the workspace (re-read per layer: L1/L2 hits).  Halo pixels are written by
   // two or four overlapping tiles with identical values.
   float4* gpp = gp + (long long)b * hw + pix0;
-  float4* GPs = reinterpret_cast<float4*>(gth_acc + gth_pad + (size_t)g.L * kPx * kTiledThreads) + tid;   // [kPx][256], if it fits
+  float4* GPs = reinterpret_cast<float4*>(stash + (size_t)g.L * kPx * kTiledThreads) + tid;   // [kPx][256], if it fits
 
   // ---- pre-pass: T_l and A from the saved alpha samples ---------------------------------------------
   {
@@ -203,16 +202,23 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
     float Tc[kPx], A[kPx];
 #pragma unroll
     for (int k = 0; k < kPx; ++k) { Tc[k] = 1.f; A[k] = 0.f; }
+    // running pointers (front layer first): keeps the loop free of 64-bit index arithmetic
+    const typename SavedAlpha<T>::type* sa[kPx];
+#pragma unroll
+    for (int k = 0; k < kPx; ++k) sa[k] = savb + (long long)(g.L - 1) * hw + k * g.W;
+    float* tp = Tst + (g.L - 1) * kPx * kTiledThreads;
     for (int l = g.L - 1; l >= 0; --l) {
 #pragma unroll
       for (int k = 0; k < kPx; ++k) {
-        Tst[(l * kPx + k) * kTiledThreads] = live[k] ? Tc[k] : 0.f;
+        tp[k * kTiledThreads] = live[k] ? Tc[k] : 0.f;
         if (live[k]) {
-          const float a = ld_alpha(savb + (long long)l * hw + k * g.W);
+          const float a = ld_alpha(sa[k]);
           A[k] = fmaf(Tc[k], a, A[k]);
           Tc[k] *= (1.f - a);
         }
+        sa[k] -= hw;
       }
+      tp -= kPx * kTiledThreads;
     }
     const float gs = g.m11 ? 2.f : 1.f, is = g.m11 ? 0.5f : 1.f, ib = g.m11 ? 0.5f : 0.f;
     const T* gob = gout + (long long)b * 4 * hw + pix0;
@@ -242,6 +248,7 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
 #pragma unroll
   for (int k = 0; k < kPx; ++k) S0[k] = S1[k] = S2[k] = R[k] = 0.f;
   float4* Gt = G + (kPx * ty) * kTW + tx;                     // this thread's records: Gt[k * kTW]
+  const bool colok = tx >= 1 && j <= g.W;                     // anchor column a in [0, W]: pixel W is virtual (record 0)
 
   for (int l = 0; l < g.L; ++l) {
     const ShiftPlan sp = splan[l];
@@ -264,6 +271,7 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
           }
         }
       }
+      if (kNeedTheta) park_theta_partials(Tst + l * kPx * kTiledThreads, 0.f, 0.f, 0.f, 0.f);
       continue;
     }
     __syncthreads();                                          // previous layer: buf readers and G readers are done
@@ -320,64 +328,61 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
         R[k] = fmaf(om, R[k], a);
       }
     }
-    if (kNeedTheta) {
-      float part[6] = {hW * accx * xj, hW * accxy, hW * accx, hH * accy * xj, hH * accyy, hH * accy};
-      const float s = warp_sum6(part, tx);
-      const int qq = warp_sum6_index(tx);
-      if ((tx & 3) == 0 && qq < 6) atomicAdd(&gth_acc[l * 6 + qq], s);
-    }
+    if (kNeedTheta) park_theta_partials(Tst + l * kPx * kTiledThreads, accx, accxy, accy, accyy);   // T_l slots are dead
     if (kNeedX) {
       __syncthreads();                                        // records of the whole tile are in G
       // anchors (a, b) = (j, ibase + k), tx >= 1, row >= 1: texel (a + X, b + Y) gets
       //   (1-fy)[(1-fx) g(a, b) + fx g(a-1, b)] + fy[(1-fx) g(a, b-1) + fx g(a-1, b-1)]
-      const bool colok = tx >= 1 && j <= g.W;                 // a in [0, W]: pixel W is virtual (its record is 0)
       const int X = j + sp.X;                                 // texel column
-      const float wx0 = (1.f - sp.fx) * zs, wx1 = sp.fx * zs, wy0 = 1.f - sp.fy, wy1 = sp.fy;
+      const bool xin = colok && (unsigned)X < (unsigned)g.W;
+      const f32x2 wx0 = bc((1.f - sp.fx) * zs), wx1 = bc(sp.fx * zs), wy0 = bc(1.f - sp.fy), wy1 = bc(sp.fy);
       T* gxl = gx + ((long long)b * g.L + l) * 4 * hw;
-      float4 hprev = make_float4(0.f, 0.f, 0.f, 0.f);
+      // CTA-uniform: can a texel at this tile's own (unshifted) coordinates be out of every pixel's reach?
+      const bool zfill = j0 + 1 - sp.X < 0 || j0 + kAnchor - sp.X > g.W || i0 + 1 - sp.Y < 0 || i0 + kAnchor - sp.Y > g.H;
+      f32x2 hp_rg = bc(0.f), hp_ba = bc(0.f);
       if (tx >= 1 && ty >= 1) {                               // row kPx*ty - 1 is inside the tile
         const float4 c = Gt[-kTW], d = Gt[-kTW - 1];
-        hprev = make_float4(wx0 * c.x + wx1 * d.x, wx0 * c.y + wx1 * d.y, wx0 * c.z + wx1 * d.z, wx0 * c.w + wx1 * d.w);
+        hp_rg = fma2(wx1, pk(d.x, d.y), mul2(wx0, pk(c.x, c.y)));
+        hp_ba = fma2(wx1, pk(d.z, d.w), mul2(wx0, pk(c.z, c.w)));
       }
 #pragma unroll
       for (int k = 0; k < kPx; ++k) {
-        float4 hcur = make_float4(0.f, 0.f, 0.f, 0.f);
+        f32x2 hc_rg = bc(0.f), hc_ba = bc(0.f);
         if (tx >= 1) {
           const float4 c = Gt[k * kTW], d = Gt[k * kTW - 1];
-          hcur = make_float4(wx0 * c.x + wx1 * d.x, wx0 * c.y + wx1 * d.y, wx0 * c.z + wx1 * d.z, wx0 * c.w + wx1 * d.w);
+          hc_rg = fma2(wx1, pk(d.x, d.y), mul2(wx0, pk(c.x, c.y)));
+          hc_ba = fma2(wx1, pk(d.z, d.w), mul2(wx0, pk(c.z, c.w)));
         }
         const int brow = ibase + k;                           // anchor row b
         const bool rowok = (kPx * ty + k) >= 1 && brow <= g.H;
-        if (colok && rowok) {
-          const int Y = brow + sp.Y;
-          if ((unsigned)X < (unsigned)g.W && (unsigned)Y < (unsigned)g.H) {
-            T* o = gxl + Y * g.W + X;
-            st(o, wy0 * hcur.x + wy1 * hprev.x);
-            st(o + hw, wy0 * hcur.y + wy1 * hprev.y);
-            st(o + 2 * hw, wy0 * hcur.z + wy1 * hprev.z);
-            st(o + 3 * hw, wy0 * hcur.w + wy1 * hprev.w);
-          }
-          // the same coordinates taken as a TEXEL of this layer: if no pixel touches it, it is ours to zero
-          if (j < g.W && brow < g.H) {
-            const int pa = j - sp.X, pb = brow - sp.Y;        // the anchor that would own texel (j, brow)
-            if (pa < 0 || pa > g.W || pb < 0 || pb > g.H) {
-              T* o = gxl + brow * g.W + j;
-              st(o, 0.f); st(o + hw, 0.f); st(o + 2 * hw, 0.f); st(o + 3 * hw, 0.f);
-            }
+        const int Y = brow + sp.Y;
+        if (xin && rowok && (unsigned)Y < (unsigned)g.H) {
+          float v0, v1, v2, v3;
+          upk(fma2(wy1, hp_rg, mul2(wy0, hc_rg)), v0, v1);
+          upk(fma2(wy1, hp_ba, mul2(wy0, hc_ba)), v2, v3);
+          T* o = gxl + (Y * g.W + X);
+          st(o, v0); st(o + hw, v1); st(o + 2 * hw, v2); st(o + 3 * hw, v3);
+        }
+        // the same coordinates taken as a TEXEL of this layer: if no pixel touches it, it is ours to zero
+        if (zfill && colok && rowok && j < g.W && brow < g.H) {
+          const int pa = j - sp.X, pb = brow - sp.Y;          // the anchor that would own texel (j, brow)
+          if (pa < 0 || pa > g.W || pb < 0 || pb > g.H) {
+            T* o = gxl + (brow * g.W + j);
+            st(o, 0.f); st(o + hw, 0.f); st(o + 2 * hw, 0.f); st(o + 3 * hw, 0.f);
           }
         }
-        hprev = hcur;
+        hp_rg = hc_rg; hp_ba = hc_ba;
       }
     }
   }
   if (kNeedTheta) {
     __syncthreads();
-    for (int k = tid; k < g.L * 6; k += kTiledThreads) atomicAdd(gtheta + (long long)b * g.L * 6 + k, gth_acc[k]);
+    reduce_theta_partials(stash, g.L, tid, xj, hW, hH, gtheta + (long long)b * g.L * 6);
   }
 }
 
 inline size_t shift_bwd_smem_bytes(int L, size_t vec_bytes) {
-  return vec_bytes * kShiftCap + sizeof(float4) * kTW * kTH + sizeof(ShiftPlan) * L + sizeof(float) * ((6 * L + 3) & ~3) +
+  return vec_bytes * kShiftCap + sizeof(float4) * kTW * kTH + sizeof(ShiftPlan) * L +
          sizeof(float) * (size_t)L * kPx * kTiledThreads;
 }
 

@@ -28,6 +28,7 @@ constexpr int kTW = 32, kTH = 32;           // output tile
 constexpr int kTiledThreads = 256;          // 8 warps; thread (tx, ty) owns pixels (tx, ty + kRowStep * k), k < kPx
 constexpr int kPx = kTW * kTH / kTiledThreads;
 constexpr int kRowStep = kTiledThreads / kTW;
+__host__ __device__ constexpr size_t align16(size_t n) { return (n + 15) & ~(size_t)15; }
 constexpr int kCapTexels = 2816;            // staging capacity (e.g. a 52 x 54 footprint)
 
 enum { kSkip = 0, kStaged = 1, kDirect = 2 };
@@ -243,6 +244,41 @@ __device__ __forceinline__ SampleGrad sample_staged_grad(const typename Texel<T>
   s.dx_rg = fma2(fy2, sub2(dxb_rg, dxt_rg), dxt_rg);
   s.dx_ba = fma2(fy2, sub2(dxb_ba, dxt_ba), dxt_ba);
   return s;
+}
+
+// ---- theta-gradient reduction of the tiled backward kernels --------------------------------------------
+// During the layer sweep a thread parks its four partial sums (sum dix, sum dix*y_i, sum diy, sum diy*y_i over its
+// pixels) of layer l in the four shared-memory slots that held its transmittances T_l: they are dead once the layer
+// has been swept, and the owner is the only thread that ever touched them, so no barrier is needed.  After the sweep
+// (and one barrier) warp w folds layers w, w + 8, ...: lane t adds the eight threads of column t (they share x_j),
+// forms the six affine coefficients' terms and the warp finishes with one transposing butterfly and six global
+// atomics per (CTA, layer) -- instead of a butterfly plus shared-memory atomics per (warp, layer).
+__device__ __forceinline__ void park_theta_partials(float* Tst_l, float accx, float accxy, float accy, float accyy) {
+  Tst_l[0 * kTiledThreads] = accx;
+  Tst_l[1 * kTiledThreads] = accxy;
+  Tst_l[2 * kTiledThreads] = accy;
+  Tst_l[3 * kTiledThreads] = accyy;
+}
+// `stash` = base of the [L][kPx][kTiledThreads] array (NOT offset by tid); call after __syncthreads()
+__device__ __forceinline__ void reduce_theta_partials(const float* stash, int L, int tid, float xj, float hW, float hH,
+                                                      float* __restrict__ gth) {
+  static_assert(kPx == 4, "four partial sums are parked in the kPx slots of a layer");
+  const int lane = tid & 31;
+  for (int l = tid >> 5; l < L; l += kTiledThreads / 32) {
+    float v[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float* s = stash + (l * kPx + q) * kTiledThreads + lane;
+      float a = 0.f;
+#pragma unroll
+      for (int r = 0; r < kTiledThreads / 32; ++r) a += s[32 * r];
+      v[q] = a;
+    }
+    const float part[6] = {hW * v[0] * xj, hW * v[1], hW * v[0], hH * v[2] * xj, hH * v[3], hH * v[2]};
+    const float sum = warp_sum6(part, lane);
+    const int q = warp_sum6_index(lane);
+    if ((lane & 3) == 0 && q < 6) atomicAdd(gth + l * 6 + q, sum);
+  }
 }
 
 }  // namespace mgr
