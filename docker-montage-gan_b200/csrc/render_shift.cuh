@@ -200,6 +200,19 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
   {
     float GP0[kPx], GP1[kPx], GP2[kPx], GA[kPx];
     float Tc[kPx], A[kPx];
+    // upstream gradient and forward output: issued first so that their latency hides behind the alpha sweep
+    float gv[kPx][4], ov[kPx][3];
+    {
+      const T* gob = gout + (long long)b * 4 * hw + pix0;
+      const T* ob_ = out + (long long)b * 4 * hw + pix0;
+#pragma unroll
+      for (int k = 0; k < kPx; ++k) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) gv[k][c] = live[k] ? ld(gob + k * g.W + c * hw) : 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) ov[k][c] = live[k] ? ld(ob_ + k * g.W + c * hw) : 0.f;
+      }
+    }
 #pragma unroll
     for (int k = 0; k < kPx; ++k) { Tc[k] = 1.f; A[k] = 0.f; }
     // running pointers (front layer first): keeps the loop free of 64-bit index arithmetic
@@ -220,19 +233,18 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
       }
       tp -= kPx * kTiledThreads;
     }
-    const float gs = g.m11 ? 2.f : 1.f, is = g.m11 ? 0.5f : 1.f, ib = g.m11 ? 0.5f : 0.f;
-    const T* gob = gout + (long long)b * 4 * hw + pix0;
-    const T* ob_ = out + (long long)b * 4 * hw + pix0;
+    const float gs = g.m11 ? 2.f : 1.f;                       // d out / d o
+    const float is = g.m11 ? 0.5f : 1.f, ib = g.m11 ? 0.5f : 0.f;
 #pragma unroll
     for (int k = 0; k < kPx; ++k) {
       GP0[k] = GP1[k] = GP2[k] = GA[k] = 0.f;
       if (live[k]) {
-        const float g0 = gs * ld(gob + k * g.W), g1 = gs * ld(gob + k * g.W + hw),
-                    g2 = gs * ld(gob + k * g.W + 2 * hw), g3 = gs * ld(gob + k * g.W + 3 * hw);
+        const float g0 = gs * gv[k][0], g1 = gs * gv[k][1],
+                    g2 = gs * gv[k][2], g3 = gs * gv[k][3];
         if (A[k] != 0.f) {
           const float inv = 1.f / A[k];
-          const float o0 = fmaf(ld(ob_ + k * g.W), is, ib), o1 = fmaf(ld(ob_ + k * g.W + hw), is, ib),
-                      o2 = fmaf(ld(ob_ + k * g.W + 2 * hw), is, ib);
+          const float o0 = fmaf(ov[k][0], is, ib), o1 = fmaf(ov[k][1], is, ib),
+                      o2 = fmaf(ov[k][2], is, ib);
           GP0[k] = g0 * inv; GP1[k] = g1 * inv; GP2[k] = g2 * inv;
           GA[k] = g3 - (g0 * o0 + g1 * o1 + g2 * o2) * inv;
         }
