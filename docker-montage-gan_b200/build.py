@@ -26,7 +26,8 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
-] + (["-DMGR_EXPERIMENT_NO_STAGE_LOADS"] if os.environ.get("MGR_EXPERIMENT_NO_STAGE_LOADS") else [])
+] + (["-DMGR_EXPERIMENT_NO_STAGE_LOADS"] if os.environ.get("MGR_EXPERIMENT_NO_STAGE_LOADS") else []) \
+  + os.environ.get("MGR_NVCC_DEFINES", "").split()      # developer knob for A/B builds (tools/ab.py); part of the hash
 
 
 def _nvcc():

@@ -279,16 +279,24 @@ int mgr_render_fwd_bwd_host(const void* h_x, const float* h_theta, const void* h
   MGR_CUDA(cudaStreamWaitEvent(s_in, start, 0));
   MGR_CUDA(cudaStreamWaitEvent(s_out, start, 0));
   int rc = MGR_OK;
-  const int nchunks = (B + chunk_B - 1) / chunk_B;
-  for (int c = 0; c < nchunks && rc == MGR_OK; ++c) {
-    const int k = c & 1, b0 = c * chunk_B, cb = (B - b0 < chunk_B) ? B - b0 : chunk_B;
+  // The last D2H runs with the H2D engine idle (and the first H2D with the D2H engine idle), so the tail of the
+  // batch is cut into progressively smaller chunks: chunk_B, ..., chunk_B/2, chunk_B/4, chunk_B/4.
+  const int min_cb = chunk_B >= 4 ? chunk_B / 4 : 1;
+  int b0 = 0;
+  for (int c = 0; b0 < B && rc == MGR_OK; ++c) {
+    const int k = c & 1, left = B - b0;
+    int cb = left < chunk_B ? left : chunk_B;
+    if (left <= chunk_B && cb > min_cb) cb = (cb / 2 > min_cb) ? cb / 2 : min_cb;
     const HostSlot& S = slot[k];
-    if (c >= 2) MGR_CUDA(cudaStreamWaitEvent(s_in, freed[k], 0));          // slot drained by the D2H of chunk c-2
+    // The slot's INPUT buffers are free once the kernels of chunk c-2 have run; its OUTPUT buffers once the D2H of
+    // chunk c-2 has drained them.  Waiting for each separately keeps both copy engines busy back to back.
+    if (c >= 2) MGR_CUDA(cudaStreamWaitEvent(s_in, comp[k], 0));
     MGR_CUDA(cudaMemcpyAsync(S.x, (const char*)h_x + b0 * sx, cb * sx, cudaMemcpyHostToDevice, s_in));
     MGR_CUDA(cudaMemcpyAsync(S.theta, (const char*)h_theta + b0 * st_, cb * st_, cudaMemcpyHostToDevice, s_in));
     MGR_CUDA(cudaMemcpyAsync(S.go, (const char*)h_grad_out + b0 * so, cb * so, cudaMemcpyHostToDevice, s_in));
     MGR_CUDA(cudaEventRecord(h2d[k], s_in));
     MGR_CUDA(cudaStreamWaitEvent(user, h2d[k], 0));
+    if (c >= 2) MGR_CUDA(cudaStreamWaitEvent(user, freed[k], 0));
     rc = mgr_render_forward(S.x, nullptr, (const float*)S.theta, S.out, S.sav, cb, L, H, W, dtype, range_mode, user);
     if (rc == MGR_OK)
       rc = mgr_render_backward(S.x, nullptr, (const float*)S.theta, S.out, S.go, S.sav, S.gx, (float*)S.gt, S.ws,
@@ -301,6 +309,7 @@ int mgr_render_fwd_bwd_host(const void* h_x, const float* h_theta, const void* h
     MGR_CUDA(cudaMemcpyAsync((char*)h_grad_x + b0 * sx, S.gx, cb * sx, cudaMemcpyDeviceToHost, s_out));
     MGR_CUDA(cudaMemcpyAsync((char*)h_grad_theta + b0 * st_, S.gt, cb * st_, cudaMemcpyDeviceToHost, s_out));
     MGR_CUDA(cudaEventRecord(freed[k], s_out));
+    b0 += cb;
   }
   // `user` completes only when the last results have landed on the host
   if (rc == MGR_OK) {
