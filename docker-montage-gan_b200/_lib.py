@@ -41,6 +41,7 @@ SYMBOLS = {
     "mgr_translation_to_theta": (_i, [_vp, _vp, _c.c_longlong, _vp]),
     "mgr_pad_stack_layer": (_i, [_vp, _i64p, _vp, _i, _i, _i, _i, _i, _i, _i, _c.c_float, _i, _vp]),
     "mgr_composite_jvp": (_i, [_vp, _i64p, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "mgr_composite_u8": (_i, [_vp, _i64p, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mgr_render_host_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "mgr_render_fwd_bwd_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mgr_render_backward": (_i, [_vp, _i64p, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp]),

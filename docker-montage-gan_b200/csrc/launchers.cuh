@@ -6,6 +6,7 @@
 #include "render_shift.cuh"
 #include "render_tiled.cuh"
 #include "warp_ops.cuh"
+#include "pil_composite.cuh"
 
 namespace mgr {
 
@@ -230,6 +231,23 @@ int launch_composite_jvp(const void* x, const void* tx, void* tout, const Geomet
   return MGR_OK;
 }
 
+template <typename T>
+int launch_pil_composite(const void* x, float* out_f32, uint8_t* out_u8, const Geometry& g, cudaStream_t s) {
+  // four pixels per thread when rows, planes and bases are 4-element aligned (the reference's contiguous layout is)
+  const bool vec = g.W % 4 == 0 && g.sh % 4 == 0 && g.sc % 4 == 0 && g.sl % 4 == 0 && g.sb % 4 == 0 &&
+                   reinterpret_cast<uintptr_t>(x) % (4 * sizeof(T)) == 0 &&
+                   (!out_f32 || reinterpret_cast<uintptr_t>(out_f32) % 16 == 0) &&
+                   (!out_u8 || reinterpret_cast<uintptr_t>(out_u8) % 4 == 0);
+  const long long total = (long long)g.B * g.H * (vec ? g.W / 4 : g.W);
+  const long long blocks = (total + 255) / 256;
+  const unsigned grid = (unsigned)(blocks < 148 * 16 ? blocks : 148 * 16);     // grid-stride, 16 CTAs per SM at most
+  if (vec) pil_composite_kernel<T, 4><<<grid, 256, 0, s>>>((const T*)x, out_f32, out_u8, g);
+  else pil_composite_kernel<T, 1><<<grid, 256, 0, s>>>((const T*)x, out_f32, out_u8, g);
+  MGR_CUDA(cudaGetLastError());
+  count_launch();
+  return MGR_OK;
+}
+
 }  // namespace mgr
 
 #include "launchers_decl.h"
@@ -255,4 +273,7 @@ int launch_composite_jvp(const void* x, const void* tx, void* tout, const Geomet
   }                                                                                                          \
   int mgr_jvp_##SUFFIX(const void* x, const void* tx, void* tout, const mgr::Geometry& g, cudaStream_t s) {  \
     return mgr::launch_composite_jvp<T>(x, tx, tout, g, s);                                                  \
+  }                                                                                                          \
+  int mgr_pil_##SUFFIX(const void* x, float* of, unsigned char* ou, const mgr::Geometry& g, cudaStream_t s) { \
+    return mgr::launch_pil_composite<T>(x, of, ou, g, s);                                                    \
   }

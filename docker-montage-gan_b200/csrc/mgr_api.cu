@@ -225,6 +225,20 @@ int mgr_composite_jvp(const void* x, const int64_t* x_strides, const void* tange
   }
 }
 
+int mgr_composite_u8(const void* x, const int64_t* x_strides, float* out_f32, unsigned char* out_u8, int B, int L, int H,
+                     int W, int dtype, int range_mode, void* stream) {
+  mgr::Geometry g;
+  if (int rc = check_common(x, x_strides, B, L, H, W, dtype, range_mode, &g)) return rc;
+  if (!out_f32 && !out_u8) return fail(MGR_ERR_INVALID_ARGUMENT, "out_f32 and out_u8 are both NULL");
+  if (B == 0) return MGR_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case MGR_F32: return mgr_pil_f32(x, out_f32, out_u8, g, s);
+    case MGR_BF16: return mgr_pil_bf16(x, out_f32, out_u8, g, s);
+    default: return mgr_pil_f16(x, out_f32, out_u8, g, s);
+  }
+}
+
 // ---- end-to-end entry point with HOST buffers: chunked, double-buffered, three streams ----------------
 namespace {
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }

@@ -177,6 +177,33 @@ def alpha_composite_pytorch(blchw_lchw: torch.Tensor, use_premultiplied: bool = 
     return render(blchw_lchw, None, in_range="01")
 
 
+def alpha_composite(blchw_lchw: torch.Tensor, *, in_range: str = "01", return_bytes: bool = False):
+    """Drop-in for ``custom_utils.image_utils.alpha_composite`` (``image_utils.py:74-96``), the non-differentiable
+    Pillow composite behind snapshots, metrics and the renderer-training targets: every layer is quantised to bytes
+    (``trunc(v * 255)``), composited back to front with Pillow's integer "over", and returned as ``byte / 255``.
+    Bit-exact with that path (tests/golden/pil_composite_golden.npz), without its D2H copy, per-sample / per-layer
+    Python loop and H2D copy.
+
+    ``[B,L,4,H,W]`` -> ``[B,4,H,W]`` fp32 on the input's device (``[L,4,H,W]`` -> ``[4,H,W]``), range [0,1].
+    ``in_range='m11'`` folds the callers' ``normalize_zero1`` (``loss_aio.py:351``) into the kernel;
+    ``return_bytes=True`` additionally returns the uint8 canvas.
+    """
+    x = blchw_lchw.unsqueeze(0) if blchw_lchw.dim() == 4 else blchw_lchw
+    _check_inputs(x, None, in_range)
+    lib = _lib.load()
+    B, L, _, H, W = x.shape
+    xk, strides = _x_arg(x.detach())
+    out = torch.empty((B, 4, H, W), dtype=torch.float32, device=x.device)
+    u8 = torch.empty((B, 4, H, W), dtype=torch.uint8, device=x.device) if return_bytes else None
+    with torch.cuda.device(x.device):
+        rc = lib.mgr_composite_u8(_ptr(xk), strides, _ptr(out), _ptr(u8), B, L, H, W, _DTYPES[x.dtype], _RANGES[in_range],
+                                  _stream_ptr(x.device))
+    _lib.check(rc, "mgr_composite_u8")
+    if blchw_lchw.dim() == 4:
+        out, u8 = out[0], (None if u8 is None else u8[0])
+    return (out, u8) if return_bytes else out
+
+
 # --------------------------------------------------------------------------------------------------
 # materialised warp (SURVEY.md 8a row a1) and the caller-side helpers (rows a4, a10, a12)
 # --------------------------------------------------------------------------------------------------

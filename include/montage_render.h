@@ -161,6 +161,19 @@ int mgr_composite_jvp(const void* x, const int64_t* x_strides, const void* tange
                       int B, int L, int H, int W, int dtype, int range_mode, void* stream);
 
 /*
+ * Non-differentiable 8-bit composite, bit-exact with the reference's Pillow path
+ * (custom_utils/image_utils.py:74-96 alpha_composite: ToPILImage -> Image.alpha_composite per layer -> ToTensor;
+ * callers custom/loss_aio.py:351,362, custom/training_loop_aio.py:531,765,775, metrics/metric_utils.py:233,304).
+ *   x        [B,L,4,H,W] as in mgr_render_forward (any dtype; MGR_RANGE_M11 applies normalize_zero1 first,
+ *            image_utils.py:184-187), layer 0 = back
+ *   out_f32  [B,4,H,W] fp32 = byte / 255 (what the reference returns), or NULL
+ *   out_u8   [B,4,H,W] uint8 canvas bytes (for PNG snapshots without a second pass), or NULL -- not both NULL
+ * Bytes are trunc(v * 255) of the fp32 value; values outside [0,1] saturate (the reference's cast wraps there).
+ */
+int mgr_composite_u8(const void* x, const int64_t* x_strides, float* out_f32, unsigned char* out_u8,
+                     int B, int L, int H, int W, int dtype, int range_mode, void* stream);
+
+/*
  * End to end with HOST buffers: out, grad_x, grad_theta = fwd+bwd(x, theta, grad_out), everything in
  * (preferably pinned) host memory, laid out exactly like the device tensors.  The batch is cut
  * into chunks of chunk_B samples that flow through two device slots on three streams (H2D copy,

@@ -386,3 +386,55 @@ def render_fwd_bwd(x, theta, grad_out, in_range: str = "m11", dtype=np.float32):
     gimg, ggx, ggy = grid_sample_bwd((B * L, C, H, W), aux, gw.reshape(B * L, C, H, W))
     gtheta = affine_grid_bwd(ggx, ggy, dt).reshape(B, L, 2, 3)
     return dict(out=out, grad_x=gimg.reshape(x.shape), grad_theta=gtheta, nan_mask=nan_mask)
+
+
+# ---- the non-differentiable Pillow composite (custom_utils/image_utils.py:74-96) -----------------------------
+# The integer "over" lives in a third-party dependency that is not under /root/reference: Pillow
+# (libImaging/AlphaComposite.c; 12.2.0 installed in this image, the reference pins none).  Restated here from its
+# published algorithm and pinned against Pillow itself, through the reference's own function, by
+# tests/golden/pil_composite_golden.npz (oracle/make_golden_pil.py).
+
+def pil_to_byte(v01) -> np.ndarray:
+    """``ToPILImage`` on a float tensor: ``trunc(v * 255)`` with the product in fp32 (torchvision
+    ``functional.to_pil_image``: ``pic.mul(255).byte()`` / ``(npimg * 255).astype(np.uint8)``).  Values outside
+    [0,1] saturate here (the cast wraps there; the reference never feeds such values)."""
+    s = np.asarray(v01, np.float32) * np.float32(255)
+    return np.clip(np.trunc(np.nan_to_num(s, nan=0.0)), 0, 255).astype(np.uint8)
+
+
+def pil_over(dst: np.ndarray, src: np.ndarray) -> np.ndarray:
+    """``dst.alpha_composite(src)`` on uint8 RGBA arrays [...,4] (channel last), Pillow's integer arithmetic:
+    7 extra precision bits, divisions by 255 as ``((a >> 8) + a) >> 8``, transparent source copies dst."""
+    d = dst.astype(np.uint32)
+    s = src.astype(np.uint32)
+    da, sa = d[..., 3], s[..., 3]
+    blend = da * (255 - sa)
+    outa255 = sa * 255 + blend
+    coef1 = sa * 255 * 255 * 128 // np.where(outa255 == 0, 1, outa255)
+    coef2 = 255 * 128 - coef1
+    out = np.empty_like(d)
+    for c in range(3):
+        t = s[..., c] * coef1 + d[..., c] * coef2 + (0x80 << 7)
+        out[..., c] = (((t >> 8) + t) >> 8) >> 7
+    t = outa255 + 0x80
+    out[..., 3] = ((t >> 8) + t) >> 8
+    return np.where((sa == 0)[..., None], d, out).astype(np.uint8)
+
+
+def pil_alpha_composite(x, in_range: str = "01"):
+    """``image_utils.alpha_composite`` on ``[B,L,4,H,W]`` (or ``[L,4,H,W]``): returns (fp32 ``byte / 255``
+    ``[B,4,H,W]``, the uint8 canvas).  ``in_range='m11'`` applies ``normalize_zero1`` first (``(t + 1) / 2`` in
+    fp32, ``image_utils.py:184-187``), as the callers at ``custom/loss_aio.py:351,362`` do."""
+    x = np.asarray(x, np.float32)
+    unb = x.ndim == 4
+    if unb:
+        x = x[None]
+    if in_range == "m11":
+        x = ((x + np.float32(1)) / np.float32(2)).astype(np.float32)
+    b = np.moveaxis(pil_to_byte(x), 2, -1)                   # [B,L,H,W,4]
+    canvas = b[:, 0]
+    for l in range(1, b.shape[1]):
+        canvas = pil_over(canvas, b[:, l])
+    u8 = np.moveaxis(canvas, -1, 1)                          # [B,4,H,W]
+    out = (u8.astype(np.float32) / np.float32(255)).astype(np.float32)
+    return (out[0], u8[0]) if unb else (out, u8)
