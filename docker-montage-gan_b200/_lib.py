@@ -25,6 +25,14 @@ _c = ctypes
 _vp, _i, _sz = _c.c_void_p, _c.c_int, _c.c_size_t
 _i64p = _c.POINTER(_c.c_int64)
 
+class MgrLayer(_c.Structure):
+    """``MgrLayer`` of include/montage_render.h: one layer of a ragged stack (or where its gradient goes)."""
+    _fields_ = [("ptr", _vp), ("sb", _c.c_int64), ("sc", _c.c_int64), ("sh", _c.c_int64),
+                ("h", _i), ("w", _i), ("top", _i), ("left", _i)]
+
+
+_layp = _c.POINTER(MgrLayer)
+
 # name -> (restype, argtypes); every symbol include/montage_render.h declares
 SYMBOLS = {
     "mgr_abi_version": (_i, []),
@@ -41,6 +49,8 @@ SYMBOLS = {
     "mgr_translation_to_theta": (_i, [_vp, _vp, _c.c_longlong, _vp]),
     "mgr_pad_stack_layer": (_i, [_vp, _i64p, _vp, _i, _i, _i, _i, _i, _i, _i, _c.c_float, _i, _vp]),
     "mgr_composite_jvp": (_i, [_vp, _i64p, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "mgr_render_forward_ragged": (_i, [_layp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "mgr_render_backward_ragged": (_i, [_layp, _vp, _vp, _vp, _vp, _layp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mgr_composite_u8": (_i, [_vp, _i64p, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mgr_render_host_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "mgr_render_fwd_bwd_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp]),

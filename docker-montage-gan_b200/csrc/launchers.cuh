@@ -18,37 +18,84 @@ bool tiled_ok(const void* x, const Geometry& g) {
   if (debug_path() == 1) return false;
   const int v = kStageVec;
   const long long layer_bytes = (3 * g.sc + (long long)g.H * g.sh) * (long long)sizeof(T);   // 32-bit offsets inside a layer
-  return (g.W % v == 0) && (g.sh % v == 0) && (g.sc % v == 0) && (g.sl % v == 0) && (g.sb % v == 0) &&
+  return (g.L <= kMaxTiledLayers) && (g.W % v == 0) && (g.sh % v == 0) && (g.sc % v == 0) && (g.sl % v == 0) && (g.sb % v == 0) &&
          (reinterpret_cast<uintptr_t>(x) % (kStageVec * sizeof(T)) == 0) && g.sc >= 0 && (long long)g.H * g.W < (1LL << 29) && layer_bytes < (1LL << 31);
+}
+
+// the canvas layout x[B,L,4,H,W] / grad_x[B,L,4,H,W] as per-layer descriptors (every layer covers the whole canvas)
+template <typename T>
+SrcLayers canvas_src(const void* x, const Geometry& g) {
+  SrcLayers r{};
+  for (int l = 0; l < g.L && l < kMaxTiledLayers; ++l)
+    r.s[l] = SrcLayer{reinterpret_cast<const T*>(x) + (long long)l * g.sl, g.sb, g.sc, g.sh, g.H, g.W, 0, 0};
+  return r;
+}
+template <typename T>
+DstLayers canvas_dst(void* gx, const Geometry& g) {
+  DstLayers r{};
+  const long long hw = (long long)g.H * g.W;
+  for (int l = 0; l < g.L && l < kMaxTiledLayers; ++l)
+    r.s[l] = DstLayer{gx ? reinterpret_cast<T*>(gx) + (long long)l * 4 * hw : nullptr, (long long)g.L * 4 * hw, hw, g.W, g.H, g.W, 0, 0};
+  return r;
+}
+
+// Ragged stacks (one tensor per layer) only exist on the tiled path: every rectangle must satisfy
+// the vector-staging rules the canvas layout satisfies by construction.
+template <typename T>
+const char* ragged_problem(const SrcLayers& src, const DstLayers* dst, const Geometry& g) {
+  const int v = kStageVec;
+  if (g.L < 2 || g.L > kMaxTiledLayers) return "a ragged stack needs 2..32 layers";
+  if (g.W % v || (long long)g.H * g.W >= (1LL << 29)) return "canvas width must be a multiple of 4 (and H*W < 2^29)";
+  for (int l = 0; l < g.L; ++l) {
+    const SrcLayer& a = src.s[l];
+    if (!a.ptr) return "a layer pointer is NULL";
+    if (a.h < 1 || a.w < 1 || a.top < 0 || a.left < 0 || a.top + a.h > g.H || a.left + a.w > g.W) return "a layer rectangle leaves the canvas";
+    if (a.w % v || a.left % v) return "layer width and left offset must be multiples of 4";
+    if (a.sh % v || a.sc % v || a.sb % v || a.sc < 0 || a.sh < a.w) return "layer strides must be non-negative multiples of 4 elements";
+    if (reinterpret_cast<uintptr_t>(a.ptr) % (v * sizeof(T))) return "layer base pointer must be aligned to 4 elements";
+    if ((3 * a.sc + (long long)a.h * a.sh) * (long long)sizeof(T) >= (1LL << 31)) return "one layer of one sample must span < 2 GiB";
+    if (dst) {
+      const DstLayer& d = dst->s[l];
+      if (!d.ptr) return "a grad pointer is NULL";
+      if (d.h != a.h || d.w != a.w || d.top != a.top || d.left != a.left) return "grad rectangle differs from the layer's";
+      if (d.sh % 2 || d.sc % 2 || d.sb % 2 || reinterpret_cast<uintptr_t>(d.ptr) % (2 * sizeof(T))) return "grad strides / pointer must be even";
+      if (3 * d.sc + (long long)d.h * d.sh >= (1LL << 31)) return "one grad layer of one sample must span < 2^31 elements";
+    }
+  }
+  return nullptr;
+}
+
+template <typename T, bool kRagged>
+int launch_forward_tiled(const void* x, const SrcLayers& src, const float* theta, void* out, void* sav, const mgr::Geometry& g,
+                         cudaStream_t s) {
+  using Vec = typename Texel<T>::Vec;
+  const size_t smem = tiled_smem_bytes(g.L, sizeof(Vec));
+  static bool configured = false;   // per instantiation; attribute is sticky per function
+  if (!configured) {
+    MGR_CUDA(cudaFuncSetAttribute(render_fwd_tiled<T, false, kRagged>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    MGR_CUDA(cudaFuncSetAttribute(render_fwd_tiled<T, true, kRagged>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    configured = true;
+  }
+  dim3 grid((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B);
+  using SA = typename SavedAlpha<T>::type;
+  const int shift = debug_path() != 2;        // all-translation samples go to the stencil kernel
+  if (sav) render_fwd_tiled<T, true, kRagged><<<grid, kTiledThreads, smem, s>>>((const T*)x, src, theta, (T*)out, (SA*)sav, g, shift);
+  else render_fwd_tiled<T, false, kRagged><<<grid, kTiledThreads, smem, s>>>((const T*)x, src, theta, (T*)out, nullptr, g, shift);
+  if (shift) {
+    MGR_CUDA(cudaGetLastError());
+    count_launch();
+    const size_t smem2 = shift_fwd_smem_bytes(g.L, sizeof(Vec));
+    if (sav) render_fwd_shift<T, true><<<grid, kTiledThreads, smem2, s>>>(src, theta, (T*)out, (SA*)sav, g);
+    else render_fwd_shift<T, false><<<grid, kTiledThreads, smem2, s>>>(src, theta, (T*)out, nullptr, g);
+  }
+  MGR_CUDA(cudaGetLastError());
+  count_launch();
+  return MGR_OK;
 }
 
 template <typename T>
 int launch_forward(const void* x, const float* theta, void* out, void* sav, const mgr::Geometry& g, cudaStream_t s) {
-  if (theta && g.L >= 2 && tiled_ok<T>(x, g)) {
-    using Vec = typename Texel<T>::Vec;
-    const size_t smem = tiled_smem_bytes(g.L, sizeof(Vec));
-    static bool configured = false;   // per dtype instantiation; attribute is sticky per function
-    if (!configured) {
-      MGR_CUDA(cudaFuncSetAttribute(render_fwd_tiled<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      MGR_CUDA(cudaFuncSetAttribute(render_fwd_tiled<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      configured = true;
-    }
-    dim3 grid((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B);
-    using SA = typename SavedAlpha<T>::type;
-    const int shift = debug_path() != 2;        // all-translation samples go to the stencil kernel
-    if (sav) render_fwd_tiled<T, true><<<grid, kTiledThreads, smem, s>>>((const T*)x, theta, (T*)out, (SA*)sav, g, shift);
-    else render_fwd_tiled<T, false><<<grid, kTiledThreads, smem, s>>>((const T*)x, theta, (T*)out, nullptr, g, shift);
-    if (shift) {
-      MGR_CUDA(cudaGetLastError());
-      count_launch();
-      const size_t smem2 = shift_fwd_smem_bytes(g.L, sizeof(Vec));
-      if (sav) render_fwd_shift<T, true><<<grid, kTiledThreads, smem2, s>>>((const T*)x, theta, (T*)out, (SA*)sav, g);
-      else render_fwd_shift<T, false><<<grid, kTiledThreads, smem2, s>>>((const T*)x, theta, (T*)out, nullptr, g);
-    }
-    MGR_CUDA(cudaGetLastError());
-    count_launch();
-    return MGR_OK;
-  }
+  if (theta && g.L >= 2 && tiled_ok<T>(x, g)) return launch_forward_tiled<T, false>(x, canvas_src<T>(x, g), theta, out, sav, g, s);
   dim3 grid((g.W + mgr::kTileW - 1) / mgr::kTileW, (g.H + mgr::kTileH - 1) / mgr::kTileH, g.B);
   const size_t smem = sizeof(mgr::TileAffine) * g.L;
   if (theta)
@@ -85,73 +132,80 @@ int launch_backward(const void* x, const float* theta, const void* out, const vo
   return launch_backward_l<T, 32, kWarp>(x, theta, out, gout, gx32, gx, gtheta, g, flags, s);
 }
 
+// two-pass tiled backward (+ the fused stencil backward for all-translation samples): records in the workspace, no
+// atomics on grad_x; sources and gradients addressed through per-layer descriptors (canvas or ragged)
+template <typename T, bool kRagged>
+int backward_tiled(const void* x, const SrcLayers& src, const float* theta, const void* out, const void* gout, const void* sav,
+                   void* gx, const DstLayers& dst, float* gtheta, void* ws, const mgr::Geometry& g, int flags, cudaStream_t s) {
+  // two-pass tiled backward: records in the workspace, no atomics on grad_x
+  using Vec = typename Texel<T>::Vec;
+  using SA = typename SavedAlpha<T>::type;
+  const bool nx = flags & MGR_NEED_GRAD_X, nt = flags & MGR_NEED_GRAD_THETA;
+  float2* rec = reinterpret_cast<float2*>(ws);
+  float4* gp = reinterpret_cast<float4*>(reinterpret_cast<char*>(ws) + sizeof(float2) * (size_t)g.B * g.L * g.H * g.W);
+  InverseLayer* inv = reinterpret_cast<InverseLayer*>(reinterpret_cast<char*>(gp) + sizeof(float4) * (size_t)g.B * g.H * g.W);
+  int* order = reinterpret_cast<int*>(inv + (size_t)g.B * g.L);          // [B*L] + 2 counters
+  if (nt) MGR_CUDA(cudaMemsetAsync(gtheta, 0, sizeof(float) * 6 * g.B * g.L, s));
+  size_t smem = align16(tiled_smem_bytes(g.L, sizeof(Vec))) +
+                sizeof(float) * (size_t)g.L * kPx * kTiledThreads;                // + transmittance stash
+  const size_t gp_bytes = sizeof(float4) * kPx * kTiledThreads;                   // (G_P, G_A) copy, if 3 CTAs/SM still fit
+  const bool gp_smem = (smem + gp_bytes) * 3 + 3 * 1024 <= 227 * 1024;
+  if (gp_smem) smem += gp_bytes;
+  dim3 grid((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B);
+  const int shift = debug_path() != 2;
+  {
+    auto launch = [&](auto kern) -> int {
+      MGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      kern<<<grid, kTiledThreads, smem, s>>>((const T*)x, src, theta, (const T*)out, (const T*)gout, (const SA*)sav, rec, gp,
+                                             nt ? gtheta : nullptr, g, shift);
+      return MGR_OK;
+    };
+    int rc;
+    if (nt) rc = gp_smem ? launch(render_bwd_pass1<T, true, true, kRagged>) : launch(render_bwd_pass1<T, true, false, kRagged>);
+    else rc = gp_smem ? launch(render_bwd_pass1<T, false, true, kRagged>) : launch(render_bwd_pass1<T, false, false, kRagged>);
+    if (rc) return rc;
+  }
+  MGR_CUDA(cudaGetLastError());
+  count_launch();
+  if (nx) {
+    dim3 grid2((g.W + kP2W - 1) / kP2W, (g.H + kP2H - 1) / kP2H, g.B * g.L);
+    MGR_CUDA(cudaMemsetAsync(order + g.B * g.L, 0, 2 * sizeof(int), s));
+    inverse_plans_kernel<<<(g.B * g.L + 127) / 128, 128, 0, s>>>(theta, inv, g.B * g.L, g.H, g.W, order, order + g.B * g.L);
+    sample_flags_kernel<<<(g.B + 127) / 128, 128, 0, s>>>(inv, g.B, g.L);
+    MGR_CUDA(cudaGetLastError());
+    count_launch(2);
+    render_bwd_pass2<T, kRagged><<<grid2, 256, 0, s>>>(inv, order, rec, gp, (T*)gx, dst, g, shift);
+    MGR_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  if (shift) {
+    size_t smem3 = shift_bwd_smem_bytes(g.L, sizeof(Vec));
+    const bool gp_smem3 = (smem3 + gp_bytes) * 3 + 3 * 1024 <= 227 * 1024;
+    if (gp_smem3) smem3 += gp_bytes;
+    dim3 grid3((g.W + 1 + kAnchor - 1) / kAnchor, (g.H + 1 + kAnchor - 1) / kAnchor, g.B);
+    auto launch3 = [&](auto kern) -> int {
+      MGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      kern<<<grid3, kTiledThreads, smem3, s>>>(src, theta, (const T*)out, (const T*)gout, (const SA*)sav, dst,
+                                               nt ? gtheta : nullptr, gp, g);
+      return MGR_OK;
+    };
+    int rc;
+    if (nx && nt) rc = gp_smem3 ? launch3(render_bwd_shift<T, true, true, true>) : launch3(render_bwd_shift<T, true, true, false>);
+    else if (nx) rc = gp_smem3 ? launch3(render_bwd_shift<T, true, false, true>) : launch3(render_bwd_shift<T, true, false, false>);
+    else rc = gp_smem3 ? launch3(render_bwd_shift<T, false, true, true>) : launch3(render_bwd_shift<T, false, true, false>);
+    if (rc) return rc;
+    MGR_CUDA(cudaGetLastError());
+    count_launch();
+  }
+  return MGR_OK;
+}
+
 template <typename T>
 int backward_typed(const void* x, const float* theta, const void* out, const void* gout, const void* sav, void* gx,
                    float* gtheta, void* ws, const mgr::Geometry& g, int flags, cudaStream_t s) {
   const long long n = (long long)g.B * g.L * 4 * g.H * g.W;
-  if (theta && sav && g.L >= 2 && tiled_ok<T>(x, g)) {
-    // two-pass tiled backward: records in the workspace, no atomics on grad_x
-    using Vec = typename Texel<T>::Vec;
-    using SA = typename SavedAlpha<T>::type;
-    const bool nx = flags & MGR_NEED_GRAD_X, nt = flags & MGR_NEED_GRAD_THETA;
-    float2* rec = reinterpret_cast<float2*>(ws);
-    float4* gp = reinterpret_cast<float4*>(reinterpret_cast<char*>(ws) + sizeof(float2) * (size_t)g.B * g.L * g.H * g.W);
-    InverseLayer* inv = reinterpret_cast<InverseLayer*>(reinterpret_cast<char*>(gp) + sizeof(float4) * (size_t)g.B * g.H * g.W);
-    int* order = reinterpret_cast<int*>(inv + (size_t)g.B * g.L);          // [B*L] + 2 counters
-    if (nt) MGR_CUDA(cudaMemsetAsync(gtheta, 0, sizeof(float) * 6 * g.B * g.L, s));
-    size_t smem = align16(tiled_smem_bytes(g.L, sizeof(Vec))) +
-                  sizeof(float) * (size_t)g.L * kPx * kTiledThreads;                // + transmittance stash
-    const size_t gp_bytes = sizeof(float4) * kPx * kTiledThreads;                   // (G_P, G_A) copy, if 3 CTAs/SM still fit
-    const bool gp_smem = (smem + gp_bytes) * 3 + 3 * 1024 <= 227 * 1024;
-    if (gp_smem) smem += gp_bytes;
-    dim3 grid((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B);
-    const int shift = debug_path() != 2;
-    {
-      auto launch = [&](auto kern) -> int {
-        MGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        kern<<<grid, kTiledThreads, smem, s>>>((const T*)x, theta, (const T*)out, (const T*)gout, (const SA*)sav, rec, gp,
-                                               nt ? gtheta : nullptr, g, shift);
-        return MGR_OK;
-      };
-      int rc;
-      if (nt) rc = gp_smem ? launch(render_bwd_pass1<T, true, true>) : launch(render_bwd_pass1<T, true, false>);
-      else rc = gp_smem ? launch(render_bwd_pass1<T, false, true>) : launch(render_bwd_pass1<T, false, false>);
-      if (rc) return rc;
-    }
-    MGR_CUDA(cudaGetLastError());
-    count_launch();
-    if (nx) {
-      dim3 grid2((g.W + kP2W - 1) / kP2W, (g.H + kP2H - 1) / kP2H, g.B * g.L);
-      MGR_CUDA(cudaMemsetAsync(order + g.B * g.L, 0, 2 * sizeof(int), s));
-      inverse_plans_kernel<<<(g.B * g.L + 127) / 128, 128, 0, s>>>(theta, inv, g.B * g.L, g.H, g.W, order, order + g.B * g.L);
-      sample_flags_kernel<<<(g.B + 127) / 128, 128, 0, s>>>(inv, g.B, g.L);
-      MGR_CUDA(cudaGetLastError());
-      count_launch(2);
-      render_bwd_pass2<T><<<grid2, 256, 0, s>>>(inv, order, rec, gp, (T*)gx, g, shift);
-      MGR_CUDA(cudaGetLastError());
-      count_launch();
-    }
-    if (shift) {
-      size_t smem3 = shift_bwd_smem_bytes(g.L, sizeof(Vec));
-      const bool gp_smem3 = (smem3 + gp_bytes) * 3 + 3 * 1024 <= 227 * 1024;
-      if (gp_smem3) smem3 += gp_bytes;
-      dim3 grid3((g.W + 1 + kAnchor - 1) / kAnchor, (g.H + 1 + kAnchor - 1) / kAnchor, g.B);
-      auto launch3 = [&](auto kern) -> int {
-        MGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        kern<<<grid3, kTiledThreads, smem3, s>>>((const T*)x, theta, (const T*)out, (const T*)gout, (const SA*)sav,
-                                                 nx ? (T*)gx : nullptr, nt ? gtheta : nullptr, gp, g);
-        return MGR_OK;
-      };
-      int rc;
-      if (nx && nt) rc = gp_smem3 ? launch3(render_bwd_shift<T, true, true, true>) : launch3(render_bwd_shift<T, true, true, false>);
-      else if (nx) rc = gp_smem3 ? launch3(render_bwd_shift<T, true, false, true>) : launch3(render_bwd_shift<T, true, false, false>);
-      else rc = gp_smem3 ? launch3(render_bwd_shift<T, false, true, true>) : launch3(render_bwd_shift<T, false, true, false>);
-      if (rc) return rc;
-      MGR_CUDA(cudaGetLastError());
-      count_launch();
-    }
-    return MGR_OK;
-  }
+  if (theta && sav && g.L >= 2 && tiled_ok<T>(x, g))
+    return backward_tiled<T, false>(x, canvas_src<T>(x, g), theta, out, gout, sav, gx, canvas_dst<T>(gx, g), gtheta, ws, g, flags, s);
   if (theta) {
     if (flags & MGR_NEED_GRAD_THETA) MGR_CUDA(cudaMemsetAsync(gtheta, 0, sizeof(float) * 6 * g.B * g.L, s));
     float* gx32 = nullptr;
@@ -248,6 +302,20 @@ int launch_pil_composite(const void* x, float* out_f32, uint8_t* out_u8, const G
   return MGR_OK;
 }
 
+// ---- ragged stacks: one [B,4,h,w] tensor per layer (tiled kernels only) -----------------------------------------
+template <typename T>
+int launch_forward_ragged(const SrcLayers& src, const float* theta, void* out, void* sav, const Geometry& g, cudaStream_t s) {
+  if (const char* why = ragged_problem<T>(src, nullptr, g)) return fail(MGR_ERR_UNSUPPORTED, "ragged stack: %s", why);
+  return launch_forward_tiled<T, true>(nullptr, src, theta, out, sav, g, s);
+}
+template <typename T>
+int launch_backward_ragged(const SrcLayers& src, const float* theta, const void* out, const void* gout, const void* sav,
+                           const DstLayers& dst, float* gtheta, void* ws, const Geometry& g, int flags, cudaStream_t s) {
+  if (const char* why = ragged_problem<T>(src, (flags & MGR_NEED_GRAD_X) ? &dst : nullptr, g))
+    return fail(MGR_ERR_UNSUPPORTED, "ragged stack: %s", why);
+  return backward_tiled<T, true>(nullptr, src, theta, out, gout, sav, nullptr, dst, gtheta, ws, g, flags, s);
+}
+
 }  // namespace mgr
 
 #include "launchers_decl.h"
@@ -276,4 +344,13 @@ int launch_pil_composite(const void* x, float* out_f32, uint8_t* out_u8, const G
   }                                                                                                          \
   int mgr_pil_##SUFFIX(const void* x, float* of, unsigned char* ou, const mgr::Geometry& g, cudaStream_t s) { \
     return mgr::launch_pil_composite<T>(x, of, ou, g, s);                                                    \
+  }                                                                                                          \
+  int mgr_fwd_ragged_##SUFFIX(const mgr::SrcLayers& src, const float* theta, void* out, void* sav,           \
+                              const mgr::Geometry& g, cudaStream_t s) {                                      \
+    return mgr::launch_forward_ragged<T>(src, theta, out, sav, g, s);                                        \
+  }                                                                                                          \
+  int mgr_bwd_ragged_##SUFFIX(const mgr::SrcLayers& src, const float* theta, const void* out, const void* gout, \
+                              const void* sav, const mgr::DstLayers& dst, float* gtheta, void* ws,           \
+                              const mgr::Geometry& g, int flags, cudaStream_t s) {                           \
+    return mgr::launch_backward_ragged<T>(src, theta, out, gout, sav, dst, gtheta, ws, g, flags, s);         \
   }

@@ -13,7 +13,12 @@
   int mgr_pad_stack_##SUFFIX(const void* src, const long long* ss, void* dst, int B, int L, int l, int h,    \
                              int w, int H, int W, float pad, cudaStream_t s);                               \
   int mgr_jvp_##SUFFIX(const void* x, const void* tx, void* tout, const mgr::Geometry& g, cudaStream_t s);   \
-  int mgr_pil_##SUFFIX(const void* x, float* of, unsigned char* ou, const mgr::Geometry& g, cudaStream_t s);
+  int mgr_pil_##SUFFIX(const void* x, float* of, unsigned char* ou, const mgr::Geometry& g, cudaStream_t s); \
+  int mgr_fwd_ragged_##SUFFIX(const mgr::SrcLayers& src, const float* theta, void* out, void* sav,           \
+                              const mgr::Geometry& g, cudaStream_t s);                                       \
+  int mgr_bwd_ragged_##SUFFIX(const mgr::SrcLayers& src, const float* theta, const void* out, const void* gout, \
+                              const void* sav, const mgr::DstLayers& dst, float* gtheta, void* ws,           \
+                              const mgr::Geometry& g, int flags, cudaStream_t s);
 MGR_DECLARE(f32)
 MGR_DECLARE(bf16)
 MGR_DECLARE(f16)

@@ -225,6 +225,70 @@ int mgr_composite_jvp(const void* x, const int64_t* x_strides, const void* tange
   }
 }
 
+namespace {
+int ragged_geometry(const MgrLayer* layers, const float* theta, int B, int L, int H, int W, int dtype, int range_mode,
+                    mgr::Geometry* g, mgr::SrcLayers* src) {
+  if (!layers) return fail(MGR_ERR_INVALID_ARGUMENT, "layers is NULL");
+  if (!theta) return fail(MGR_ERR_UNSUPPORTED, "a ragged stack needs theta (composite-only stacks use the canvas layout)");
+  if (B < 0 || L < 1 || H < 1 || W < 1)
+    return fail(MGR_ERR_INVALID_ARGUMENT, "bad shape B=%d L=%d H=%d W=%d (need B>=0, L,H,W>=1)", B, L, H, W);
+  if (dtype != MGR_F32 && dtype != MGR_BF16 && dtype != MGR_F16) return fail(MGR_ERR_INVALID_ARGUMENT, "bad dtype %d", dtype);
+  if (range_mode != MGR_RANGE_M11 && range_mode != MGR_RANGE_01) return fail(MGR_ERR_INVALID_ARGUMENT, "bad range_mode %d", range_mode);
+  if (B > 65535) return fail(MGR_ERR_UNSUPPORTED, "B=%d exceeds 65535 per call; split the batch", B);
+  if (L < 2 || L > mgr::kMaxTiledLayers) return fail(MGR_ERR_UNSUPPORTED, "a ragged stack needs 2..32 layers, got %d", L);
+  if ((long long)B * L > 65535) return fail(MGR_ERR_UNSUPPORTED, "B*L=%lld exceeds 65535 per call; split the batch", (long long)B * L);
+  g->B = B; g->L = L; g->H = H; g->W = W;
+  g->m11 = (range_mode == MGR_RANGE_M11);
+  g->sh = W; g->sc = (long long)H * W; g->sl = 4 * g->sc; g->sb = (long long)L * g->sl;     // unused by the ragged kernels
+  *src = mgr::SrcLayers{};
+  for (int l = 0; l < L; ++l)
+    src->s[l] = mgr::SrcLayer{layers[l].ptr, layers[l].sb, layers[l].sc, layers[l].sh, layers[l].h, layers[l].w, layers[l].top, layers[l].left};
+  return MGR_OK;
+}
+}  // namespace
+
+int mgr_render_forward_ragged(const MgrLayer* layers, const float* theta, void* out, void* saved_alpha, int B, int L, int H,
+                              int W, int dtype, int range_mode, void* stream) {
+  mgr::Geometry g;
+  mgr::SrcLayers src;
+  if (int rc = ragged_geometry(layers, theta, B, L, H, W, dtype, range_mode, &g, &src)) return rc;
+  if (!out) return fail(MGR_ERR_INVALID_ARGUMENT, "out is NULL");
+  if (B == 0) return MGR_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case MGR_F32: return mgr_fwd_ragged_f32(src, theta, out, saved_alpha, g, s);
+    case MGR_BF16: return mgr_fwd_ragged_bf16(src, theta, out, saved_alpha, g, s);
+    default: return mgr_fwd_ragged_f16(src, theta, out, saved_alpha, g, s);
+  }
+}
+
+int mgr_render_backward_ragged(const MgrLayer* layers, const float* theta, const void* out, const void* grad_out,
+                               const void* saved_alpha, const MgrLayer* grads, float* grad_theta, void* workspace,
+                               size_t workspace_bytes, int B, int L, int H, int W, int dtype, int range_mode, int flags,
+                               void* stream) {
+  mgr::Geometry g;
+  mgr::SrcLayers src;
+  if (int rc = ragged_geometry(layers, theta, B, L, H, W, dtype, range_mode, &g, &src)) return rc;
+  if (!out || !grad_out || !saved_alpha) return fail(MGR_ERR_INVALID_ARGUMENT, "out / grad_out / saved_alpha is NULL");
+  if ((flags & MGR_NEED_GRAD_X) && !grads) return fail(MGR_ERR_INVALID_ARGUMENT, "grads is NULL but requested");
+  if ((flags & MGR_NEED_GRAD_THETA) && !grad_theta) return fail(MGR_ERR_INVALID_ARGUMENT, "grad_theta is NULL but requested");
+  if (!(flags & (MGR_NEED_GRAD_X | MGR_NEED_GRAD_THETA))) return MGR_OK;
+  if (B == 0) return MGR_OK;
+  const size_t need = mgr_render_backward_workspace_bytes(B, L, H, W, MGR_F32, 1, flags);   // the tiled path's records only
+  if (!workspace || workspace_bytes < need)
+    return fail(MGR_ERR_WORKSPACE_TOO_SMALL, "workspace %zu bytes < required %zu", workspace_bytes, need);
+  mgr::DstLayers dst{};
+  if (flags & MGR_NEED_GRAD_X)
+    for (int l = 0; l < L; ++l)
+      dst.s[l] = mgr::DstLayer{grads[l].ptr, grads[l].sb, grads[l].sc, grads[l].sh, grads[l].h, grads[l].w, grads[l].top, grads[l].left};
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (dtype) {
+    case MGR_F32: return mgr_bwd_ragged_f32(src, theta, out, grad_out, saved_alpha, dst, grad_theta, workspace, g, flags, s);
+    case MGR_BF16: return mgr_bwd_ragged_bf16(src, theta, out, grad_out, saved_alpha, dst, grad_theta, workspace, g, flags, s);
+    default: return mgr_bwd_ragged_f16(src, theta, out, grad_out, saved_alpha, dst, grad_theta, workspace, g, flags, s);
+  }
+}
+
 int mgr_composite_u8(const void* x, const int64_t* x_strides, float* out_f32, unsigned char* out_u8, int B, int L, int H,
                      int W, int dtype, int range_mode, void* stream) {
   mgr::Geometry g;

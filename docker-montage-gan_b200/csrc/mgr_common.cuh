@@ -29,6 +29,25 @@ struct Geometry {
   int m11;                   // 1: [-1,1] range mode, 0: [0,1]
 };
 
+// Where one layer's pixels live.  The canvas layout x[B,L,4,H,W] is the special case {x + l*sl, sb, sc, sh, H, W, 0, 0};
+// the ragged layout (the local generators' outputs at native size, custom_utils/image_utils.py:216-243
+// without the padded copy) gives every layer its own [B,4,h,w] tensor centred at (left, top) of the H x W canvas.
+// Texels outside the rectangle are the padding value (-1 in m11 mode, 0 in 01 mode: transparent black), which is also
+// what padding_mode='zeros' yields outside the canvas -- so "ragged" only means "per-layer bounds and base pointer".
+constexpr int kMaxTiledLayers = 32;
+struct SrcLayer {
+  const void* ptr;           // element (b = 0, c = 0, y = 0, x = 0) of this layer
+  long long sb, sc, sh;      // element strides: batch, channel, row (column stride 1)
+  int h, w, top, left;
+};
+struct SrcLayers { SrcLayer s[kMaxTiledLayers]; };
+struct DstLayer {            // grad_x of one layer: [B,4,h,w], rows contiguous
+  void* ptr;
+  long long sb, sc, sh;
+  int h, w, top, left;
+};
+struct DstLayers { DstLayer s[kMaxTiledLayers]; };
+
 // Pixel-space placement of one layer relative to a tile origin (j0,i0), SURVEY.md A.1:
 //   ix(j,i) = a00*(j-j0) + a01*(i-i0) + (X0 + rx),  iy likewise.
 // The integer part X0/Y0 is split off in double precision so the fp32 per-pixel arithmetic only

@@ -29,9 +29,9 @@ namespace mgr {
 //   rec [B*L][H*W] float2 = (T_l a_l, d a_l)        gp [B][H*W] float4 = (G_P.rgb, G_A)
 //   inverse plans [B*L] InverseLayer (128 B each)        order [B*L] int + 2 counters
 
-template <typename T, bool kNeedTheta, bool kGPSmem>
+template <typename T, bool kNeedTheta, bool kGPSmem, bool kRagged>
 __global__ void __launch_bounds__(kTiledThreads, kGPSmem ? 3 : 2)
-render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const T* __restrict__ out,
+render_bwd_pass1(const T* __restrict__ x, const __grid_constant__ SrcLayers src, const float* __restrict__ theta, const T* __restrict__ out,
                  const T* __restrict__ gout, const typename SavedAlpha<T>::type* __restrict__ sav,
                  float2* __restrict__ rec, float4* __restrict__ gp, float* __restrict__ gtheta, Geometry g,
                  int skip_shift) {
@@ -51,12 +51,11 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
   const int j0 = blockIdx.x * kTW, i0 = blockIdx.y * kTH;
   const int tx = tid & 31, ty = tid >> 5;
   for (int l = tid; l < g.L; l += kTiledThreads)
-    plan[l] = plan_layer(theta + ((long long)b * g.L + l) * 6, g.H, g.W, j0, i0, kStageVec);
+    plan[l] = plan_layer(theta + ((long long)b * g.L + l) * 6, g.H, g.W, j0, i0, kStageVec, layer_rect<kRagged>(g, src, l));
   __syncthreads();
 
   const float zs = g.m11 ? 0.5f : 1.f;
   const f32x2 zs2 = bc(zs), zb2 = bc(g.m11 ? 0.5f : 0.f);     // z = zs * raw + zb
-  const T* xb = x + (long long)b * g.sb;
   const int hw = g.H * g.W;
   const int j = j0 + tx;
   const int pix0 = (i0 + ty) * g.W + j;                       // pixel k lives 8*k rows further down
@@ -153,10 +152,10 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
       if (kNeedTheta) park_theta_partials(Tst + l * kPx * kTiledThreads, 0.f, 0.f, 0.f, 0.f);
       continue;                              // the footprint misses the image: no texel, no theta gradient
     }
-    const T* img = xb + (long long)l * g.sl;
+    const SrcView sv_ = layer_view<T, kRagged>(x, g, src, b, l);
     if (mode == kStaged) {
       __syncthreads();
-      stage_footprint<T>(img, g, p, buf, tid);
+      stage_footprint<T>(g.m11 != 0, sv_, p, buf, tid);
       __syncthreads();
     }
     const float a01 = p.aff.a01, a11 = p.aff.a11;
@@ -178,12 +177,12 @@ render_bwd_pass1(const T* __restrict__ x, const float* __restrict__ theta, const
         upk(s.dy_rg, dyr, dyg); upk(s.dy_ba, dyb, dya);
       } else {
         // huge footprint: bounds-checked taps straight from global memory
-        const Taps tp = make_taps(p.aff, tx - kTW / 2, ty + kRowStep * k - kTH / 2, g.H, g.W, g.sh);
+        const Taps tp = make_taps(p.aff, tx - kTW / 2, ty + kRowStep * k - kTH / 2, sv_.h, sv_.w, sv_.rowbytes / sizeof(T));
         const float shift = g.m11 ? 1.f : 0.f;
         float v[4][4], zz[4];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          const T* pl = img + c * g.sc;
+          const T* pl = reinterpret_cast<const T*>(sv_.base + (size_t)c * sv_.plane);
           v[c][0] = (tp.mask & 1u) ? ld(pl + tp.o00) + shift : 0.f;
           v[c][1] = (tp.mask & 2u) ? ld(pl + tp.o01) + shift : 0.f;
           v[c][2] = (tp.mask & 4u) ? ld(pl + tp.o10) + shift : 0.f;
@@ -316,10 +315,11 @@ template <> struct Pack2<__half> {
 
 __device__ __forceinline__ float hat(float u) { return fmaxf(1.f - fabsf(u), 0.f); }
 
-template <typename T>
+template <typename T, bool kRagged>
 __global__ void __launch_bounds__(256, 4)
 render_bwd_pass2(const InverseLayer* __restrict__ plans, const int* __restrict__ order, const float2* __restrict__ rec,
-                 const float4* __restrict__ gp, T* __restrict__ gx, Geometry g, int skip_shift) {
+                 const float4* __restrict__ gp, T* __restrict__ gx, const __grid_constant__ DstLayers dst, Geometry g,
+                 int skip_shift) {
   __shared__ float s_jcf, s_icf;
   __shared__ int s_JC, s_IC, s_ok;
   const int n = order[blockIdx.z];              // b * L + l, heavy layers first
@@ -329,9 +329,17 @@ render_bwd_pass2(const InverseLayer* __restrict__ plans, const int* __restrict__
   const InverseLayer& L_ = plans[n];
   if (skip_shift && L_.all_shift) return;      // all-translation samples are written by render_bwd_shift
   const int hw = g.H * g.W;
-  const int x = x0b + 2 * tx, y = y0b + 2 * ty;                // top-left texel of this thread's 2 x 2 block
+  const int x = x0b + 2 * tx, y = y0b + 2 * ty;                // top-left texel of this thread's 2 x 2 block (canvas coordinates)
   const float zs = g.m11 ? 0.5f : 1.f;          // d z / d x_texel = zs * weight
-  T* gxp = gx + (long long)n * 4 * hw + y * g.W + x;
+  // the layer's own pixels: a rectangle of the canvas (the whole canvas in the [B,L,4,H,W] layout); left, w even
+  DstLayer dl;
+  if (kRagged) dl = dst.s[n - b * g.L];
+  else dl = DstLayer{gx + (long long)(n - b * g.L) * 4 * hw, (long long)g.L * 4 * hw, hw, g.W, g.H, g.W, 0, 0};
+  const int xl = x - dl.left, yl = y - dl.top;
+  const bool mine = (unsigned)xl < (unsigned)dl.w && yl >= -1 && yl < dl.h;      // at least one of the block's rows is inside
+  // CTA-uniform: the whole 64 x 16 texel block lies outside this layer's rectangle (small layers of a ragged stack)
+  if (x0b + kP2W <= dl.left || x0b >= dl.left + dl.w || y0b + kP2H <= dl.top || y0b >= dl.top + dl.h) return;
+  T* gxp = reinterpret_cast<T*>(dl.ptr) + (long long)b * dl.sb + (long long)yl * dl.sh + xl;
   f32x2 acc[2][2][2];                           // [row][col][rg | ba]
 #pragma unroll
   for (int q = 0; q < 8; ++q) (&acc[0][0][0])[q] = 0ull;
@@ -339,7 +347,7 @@ render_bwd_pass2(const InverseLayer* __restrict__ plans, const int* __restrict__
   if (L_.shift_only) {
     // pure translation: texel (x, y) is tap (dx, dy) of pixel (x - X - dx, y - Y - dy) with the layer-wide
     // weights (dx ? fx : 1 - fx)(dy ? fy : 1 - fy): a fixed 2 x 2 stencil; the 2 x 2 block reads 3 x 3 records
-    if (x >= g.W || y >= g.H) return;
+    if (!mine) return;
     const float wx[2] = {1.f - L_.fx, L_.fx}, wy[2] = {1.f - L_.fy, L_.fy};
     const float2* recn = rec + (long long)n * hw;
     const float4* gpb = gp + (long long)b * hw;
@@ -394,7 +402,7 @@ render_bwd_pass2(const InverseLayer* __restrict__ plans, const int* __restrict__
     const float pj = jcf + i00 * dxl + i01 * dyl, pi = icf + i10 * dxl + i11 * dyl;
     float mlo = fmaxf(ceilf(pj - rj), (float)(-JC)), mhi = fminf(floorf(pj + rj), (float)(g.W - 1 - JC));
     float nlo = fmaxf(ceilf(pi - ri), (float)(-IC)), nhi = fminf(floorf(pi + ri), (float)(g.H - 1 - IC));
-    const bool has = s_ok && x < g.W && y < g.H && mlo <= mhi && nlo <= nhi;
+    const bool has = s_ok && mine && mlo <= mhi && nlo <= nhi;
     if (!has) { mlo = 0.f; mhi = -1.f; nlo = 0.f; nhi = -1.f; }
     float x0l = dxl - 0.5f, y0l = dyl - 0.5f;                  // texel (0,0) of the block relative to the CTA centre
     const float2* rec0 = rec + (long long)n * hw + (IC * g.W + JC);
@@ -500,19 +508,19 @@ render_bwd_pass2(const InverseLayer* __restrict__ plans, const int* __restrict__
         for (int nn = n0; nn <= n1; ++nn) row(nn, mlo, mhi, x0l, y0l, acc);
       }
     }
-    if (x >= g.W || y >= g.H) return;
+    if (!mine) return;
   }
 #pragma unroll
   for (int ky = 0; ky < 2; ++ky) {
-    if (y + ky >= g.H) break;
+    if ((unsigned)(yl + ky) >= (unsigned)dl.h) continue;
     float r0, g0, b0, a0, r1, g1, b1, a1;
     upk(acc[ky][0][0], r0, g0); upk(acc[ky][0][1], b0, a0);
     upk(acc[ky][1][0], r1, g1); upk(acc[ky][1][1], b1, a1);
-    T* o = gxp + ky * g.W;
-    Pack2<T>::store(o, zs * r0, zs * r1);              // W % 4 == 0 on this path: x + 1 < W
-    Pack2<T>::store(o + hw, zs * g0, zs * g1);
-    Pack2<T>::store(o + 2 * hw, zs * b0, zs * b1);
-    Pack2<T>::store(o + 3 * hw, zs * a0, zs * a1);
+    T* o = gxp + ky * dl.sh;
+    Pack2<T>::store(o, zs * r0, zs * r1);              // w % 4 == 0 and left % 4 == 0 on this path: xl + 1 < w
+    Pack2<T>::store(o + dl.sc, zs * g0, zs * g1);
+    Pack2<T>::store(o + 2 * dl.sc, zs * b0, zs * b1);
+    Pack2<T>::store(o + 3 * dl.sc, zs * a0, zs * a1);
   }
 }
 

@@ -39,13 +39,13 @@ __device__ __forceinline__ ShiftPlan make_shift_plan(const float* __restrict__ t
 }
 
 // footprint of the pixel tile whose top-left pixel is (j0, i0) under a shift plan, as a LayerPlan
-__device__ __forceinline__ LayerPlan shift_footprint(const ShiftPlan& sp, int j0, int i0, int H, int W) {
+__device__ __forceinline__ LayerPlan shift_footprint(const ShiftPlan& sp, int j0, int i0, const SrcLayer& src) {   // src: rectangle only
   LayerPlan p;
   p.x_lo = (j0 + sp.X) & ~(kStageVec - 1);
   p.y_lo = i0 + sp.Y;
   p.bw = ((j0 + sp.X + kTW + 1) - p.x_lo + kStageVec - 1) & ~(kStageVec - 1);     // columns x_lo .. j0+X+32
   p.bh = kTH + 1;
-  const bool miss = (p.x_lo + p.bw <= 0) || (p.x_lo >= W) || (p.y_lo + p.bh <= 0) || (p.y_lo >= H);
+  const bool miss = (p.x_lo + p.bw <= src.left) || (p.x_lo >= src.left + src.w) || (p.y_lo + p.bh <= src.top) || (p.y_lo >= src.top + src.h);
   p.mode = miss ? kSkip : kStaged;
   p.lrx = p.lry = 0.f; p.pad_ = 0;
   return p;
@@ -58,7 +58,7 @@ constexpr int kShiftCap = (kTW + 2 * kStageVec) * (kTH + 1);        // staged te
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool kSave>
 __global__ void __launch_bounds__(kTiledThreads, 3)
-render_fwd_shift(const T* __restrict__ x, const float* __restrict__ theta, T* __restrict__ out,
+render_fwd_shift(const __grid_constant__ SrcLayers src, const float* __restrict__ theta, T* __restrict__ out,
                  typename SavedAlpha<T>::type* __restrict__ sav, Geometry g) {
   using Vec = typename Texel<T>::Vec;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -74,7 +74,6 @@ render_fwd_shift(const T* __restrict__ x, const float* __restrict__ theta, T* __
   __syncthreads();
 
   const f32x2 zs2 = bc(g.m11 ? 0.5f : 1.f), zb2 = bc(g.m11 ? 0.5f : 0.f);     // z = zs * raw + zb
-  const T* xb = x + (long long)b * g.sb;
   const int hw = g.H * g.W;
   const int j = j0 + tx;
   const int pix0 = (i0 + kPx * ty) * g.W + j;
@@ -87,7 +86,7 @@ render_fwd_shift(const T* __restrict__ x, const float* __restrict__ theta, T* __
 
   for (int l = 0; l < g.L; ++l) {
     const ShiftPlan sp = splan[l];
-    const LayerPlan p = shift_footprint(sp, j0, i0, g.H, g.W);
+    const LayerPlan p = shift_footprint(sp, j0, i0, src.s[l]);
     typename SavedAlpha<T>::type* sv = nullptr;
     if (kSave) sv = sav + ((long long)b * g.L + l) * hw + pix0;
     if (p.mode == kSkip) {
@@ -99,7 +98,7 @@ render_fwd_shift(const T* __restrict__ x, const float* __restrict__ theta, T* __
       continue;
     }
     __syncthreads();
-    stage_footprint<T>(xb + (long long)l * g.sl, g, p, buf, tid);
+    stage_footprint<T>(g.m11 != 0, src_view<T>(src.s[l], b), p, buf, tid);
     __syncthreads();
     const f32x2 fx2 = bc(sp.fx), fy2 = bc(sp.fy);
     const Vec* q = buf + (kPx * ty) * p.bw + (tx + j0 + sp.X - p.x_lo);
@@ -155,9 +154,9 @@ constexpr int kAnchor = kTW - 1;
 
 template <typename T, bool kNeedX, bool kNeedTheta, bool kGPSmem>
 __global__ void __launch_bounds__(kTiledThreads, kGPSmem ? 3 : 2)
-render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const T* __restrict__ out,
+render_bwd_shift(const __grid_constant__ SrcLayers src, const float* __restrict__ theta, const T* __restrict__ out,
                  const T* __restrict__ gout, const typename SavedAlpha<T>::type* __restrict__ sav,
-                 T* __restrict__ gx, float* __restrict__ gtheta, float4* __restrict__ gp, Geometry g) {
+                 const __grid_constant__ DstLayers dst, float* __restrict__ gtheta, float4* __restrict__ gp, Geometry g) {
   using Vec = typename Texel<T>::Vec;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Vec* buf = reinterpret_cast<Vec*>(smem_raw);                                           // [kShiftCap]
@@ -177,7 +176,6 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
 
   const float zs = g.m11 ? 0.5f : 1.f;
   const f32x2 zs2 = bc(zs), zb2 = bc(g.m11 ? 0.5f : 0.f);
-  const T* xb = x + (long long)b * g.sb;
   const int hw = g.H * g.W;
   const int j = j0 + tx;
   const int ibase = i0 + kPx * ty;
@@ -226,8 +224,8 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
         tp[k * kTiledThreads] = live[k] ? Tc[k] : 0.f;
         if (live[k]) {
           const float a = ld_alpha(sa[k]);
-          A[k] = fmaf(Tc[k], a, A[k]);
-          Tc[k] *= (1.f - a);
+          A[k] = __fmaf_rn(Tc[k], a, A[k]);
+          Tc[k] = __fmul_rn(Tc[k], __fsub_rn(1.f, a));
         }
         sa[k] -= hw;
       }
@@ -239,14 +237,17 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
     for (int k = 0; k < kPx; ++k) {
       GP0[k] = GP1[k] = GP2[k] = GA[k] = 0.f;
       if (live[k]) {
-        const float g0 = gs * gv[k][0], g1 = gs * gv[k][1],
-                    g2 = gs * gv[k][2], g3 = gs * gv[k][3];
+        const float g0 = __fmul_rn(gs, gv[k][0]), g1 = __fmul_rn(gs, gv[k][1]),
+                    g2 = __fmul_rn(gs, gv[k][2]), g3 = __fmul_rn(gs, gv[k][3]);
         if (A[k] != 0.f) {
           const float inv = 1.f / A[k];
-          const float o0 = fmaf(ov[k][0], is, ib), o1 = fmaf(ov[k][1], is, ib),
-                      o2 = fmaf(ov[k][2], is, ib);
-          GP0[k] = g0 * inv; GP1[k] = g1 * inv; GP2[k] = g2 * inv;
-          GA[k] = g3 - (g0 * o0 + g1 * o1 + g2 * o2) * inv;
+          const float o0 = __fmaf_rn(ov[k][0], is, ib), o1 = __fmaf_rn(ov[k][1], is, ib),
+                      o2 = __fmaf_rn(ov[k][2], is, ib);
+          // Explicitly rounded steps: a halo pixel is computed by up to four overlapping CTAs (as different unrolled
+          // instances k), and when (G_P, G_A) lives in global memory they all store it to the same address -- the
+          // stores must carry identical bits, so the compiler may not contract or re-associate per instance.
+          GP0[k] = __fmul_rn(g0, inv); GP1[k] = __fmul_rn(g1, inv); GP2[k] = __fmul_rn(g2, inv);
+          GA[k] = __fsub_rn(g3, __fmul_rn(__fmaf_rn(g2, o2, __fmaf_rn(g1, o1, __fmul_rn(g0, o0))), inv));
         }
       }
       if (kGPSmem) GPs[k * kTiledThreads] = make_float4(GP0[k], GP1[k], GP2[k], GA[k]);
@@ -264,21 +265,23 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
 
   for (int l = 0; l < g.L; ++l) {
     const ShiftPlan sp = splan[l];
-    const LayerPlan p = shift_footprint(sp, j0, i0, g.H, g.W);
+    const LayerPlan p = shift_footprint(sp, j0, i0, src.s[l]);
     if (p.mode == kSkip) {
       // the footprint misses the image: a transparent-black layer for this tile (a = 0): the canvas is unchanged,
       // no theta gradient, and none of this tile's anchor texels lies inside the image.  What remains is to zero
       // the texels at this tile's own (unshifted) coordinates that no pixel touches.
       if (kNeedX) {
-        T* gxl = gx + ((long long)b * g.L + l) * 4 * hw;
+        const DstLayer& dl = dst.s[l];
+        T* gxl = reinterpret_cast<T*>(dl.ptr) + (long long)b * dl.sb;
+        const int xl = j - dl.left;                            // this thread's own column inside the layer's rectangle
 #pragma unroll
         for (int k = 0; k < kPx; ++k) {
-          const int brow = ibase + k;
-          if (tx >= 1 && (kPx * ty + k) >= 1 && j < g.W && brow < g.H) {
+          const int brow = ibase + k, yl = brow - dl.top;
+          if (tx >= 1 && (kPx * ty + k) >= 1 && (unsigned)xl < (unsigned)dl.w && (unsigned)yl < (unsigned)dl.h) {
             const int pa = j - sp.X, pb = brow - sp.Y;
             if (pa < 0 || pa > g.W || pb < 0 || pb > g.H) {
-              T* o = gxl + brow * g.W + j;
-              st(o, 0.f); st(o + hw, 0.f); st(o + 2 * hw, 0.f); st(o + 3 * hw, 0.f);
+              T* o = gxl + yl * dl.sh + xl;
+              st(o, 0.f); st(o + dl.sc, 0.f); st(o + 2 * dl.sc, 0.f); st(o + 3 * dl.sc, 0.f);
             }
           }
         }
@@ -287,7 +290,7 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
       continue;
     }
     __syncthreads();                                          // previous layer: buf readers and G readers are done
-    stage_footprint<T>(xb + (long long)l * g.sl, g, p, buf, tid);
+    stage_footprint<T>(g.m11 != 0, src_view<T>(src.s[l], b), p, buf, tid);
     __syncthreads();
     float accx = 0.f, accxy = 0.f, accy = 0.f, accyy = 0.f;
     {
@@ -345,10 +348,13 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
       __syncthreads();                                        // records of the whole tile are in G
       // anchors (a, b) = (j, ibase + k), tx >= 1, row >= 1: texel (a + X, b + Y) gets
       //   (1-fy)[(1-fx) g(a, b) + fx g(a-1, b)] + fy[(1-fx) g(a, b-1) + fx g(a-1, b-1)]
-      const int X = j + sp.X;                                 // texel column
-      const bool xin = colok && (unsigned)X < (unsigned)g.W;
+      const DstLayer& dl = dst.s[l];
+      const int X = j + sp.X - dl.left;                       // texel column inside the layer's rectangle
+      const bool xin = colok && (unsigned)X < (unsigned)dl.w;
       const f32x2 wx0 = bc((1.f - sp.fx) * zs), wx1 = bc(sp.fx * zs), wy0 = bc(1.f - sp.fy), wy1 = bc(sp.fy);
-      T* gxl = gx + ((long long)b * g.L + l) * 4 * hw;
+      T* gxl = reinterpret_cast<T*>(dl.ptr) + (long long)b * dl.sb;
+      const int dsc = (int)dl.sc, dsh = (int)dl.sh;            // one layer of one sample spans < 2^31 elements (host-checked)
+      const int xl = j - dl.left;                             // own column, for the zero-fill of untouched texels
       // CTA-uniform: can a texel at this tile's own (unshifted) coordinates be out of every pixel's reach?
       const bool zfill = j0 + 1 - sp.X < 0 || j0 + kAnchor - sp.X > g.W || i0 + 1 - sp.Y < 0 || i0 + kAnchor - sp.Y > g.H;
       f32x2 hp_rg = bc(0.f), hp_ba = bc(0.f);
@@ -367,20 +373,21 @@ render_bwd_shift(const T* __restrict__ x, const float* __restrict__ theta, const
         }
         const int brow = ibase + k;                           // anchor row b
         const bool rowok = (kPx * ty + k) >= 1 && brow <= g.H;
-        const int Y = brow + sp.Y;
-        if (xin && rowok && (unsigned)Y < (unsigned)g.H) {
+        const int Y = brow + sp.Y - dl.top;
+        if (xin && rowok && (unsigned)Y < (unsigned)dl.h) {
           float v0, v1, v2, v3;
           upk(fma2(wy1, hp_rg, mul2(wy0, hc_rg)), v0, v1);
           upk(fma2(wy1, hp_ba, mul2(wy0, hc_ba)), v2, v3);
-          T* o = gxl + (Y * g.W + X);
-          st(o, v0); st(o + hw, v1); st(o + 2 * hw, v2); st(o + 3 * hw, v3);
+          T* o = gxl + (Y * dsh + X);
+          st(o, v0); st(o + dsc, v1); st(o + 2 * dsc, v2); st(o + 3 * dsc, v3);
         }
         // the same coordinates taken as a TEXEL of this layer: if no pixel touches it, it is ours to zero
-        if (zfill && colok && rowok && j < g.W && brow < g.H) {
+        const int yl = brow - dl.top;
+        if (zfill && colok && rowok && (unsigned)xl < (unsigned)dl.w && (unsigned)yl < (unsigned)dl.h) {
           const int pa = j - sp.X, pb = brow - sp.Y;          // the anchor that would own texel (j, brow)
           if (pa < 0 || pa > g.W || pb < 0 || pb > g.H) {
-            T* o = gxl + (brow * g.W + j);
-            st(o, 0.f); st(o + hw, 0.f); st(o + 2 * hw, 0.f); st(o + 3 * hw, 0.f);
+            T* o = gxl + (yl * dsh + xl);
+            st(o, 0.f); st(o + dsc, 0.f); st(o + 2 * dsc, 0.f); st(o + 3 * dsc, 0.f);
           }
         }
         hp_rg = hc_rg; hp_ba = hc_ba;

@@ -41,9 +41,9 @@ __device__ __noinline__ float4 sample_pixel_direct(const T* __restrict__ img, co
 
 // L >= 2 only (a single layer is returned untouched by the reference; the host routes L == 1 to
 // the direct kernel).  kSave: also write the sampled alpha of every (layer, pixel) to `sav`.
-template <typename T, bool kSave>
+template <typename T, bool kSave, bool kRagged>
 __global__ void __launch_bounds__(kTiledThreads, 3)
-render_fwd_tiled(const T* __restrict__ x, const float* __restrict__ theta, T* __restrict__ out,
+render_fwd_tiled(const T* __restrict__ x, const __grid_constant__ SrcLayers src, const float* __restrict__ theta, T* __restrict__ out,
                  typename SavedAlpha<T>::type* __restrict__ sav, Geometry g, int skip_shift) {
   using Vec = typename Texel<T>::Vec;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -56,11 +56,10 @@ render_fwd_tiled(const T* __restrict__ x, const float* __restrict__ theta, T* __
   const int j0 = blockIdx.x * kTW, i0 = blockIdx.y * kTH;
   const int tx = tid & 31, ty = tid >> 5;
   for (int l = tid; l < g.L; l += kTiledThreads)
-    plan[l] = plan_layer(theta + ((long long)b * g.L + l) * 6, g.H, g.W, j0, i0, kStageVec);
+    plan[l] = plan_layer(theta + ((long long)b * g.L + l) * 6, g.H, g.W, j0, i0, kStageVec, layer_rect<kRagged>(g, src, l));
   __syncthreads();
 
   const f32x2 zs2 = bc(g.m11 ? 0.5f : 1.f), zb2 = bc(g.m11 ? 0.5f : 0.f);     // z = zs * raw + zb
-  const T* xb = x + (long long)b * g.sb;
   const int hw = g.H * g.W;                                   // one plane fits 32 bits (host-checked)
   const int j = j0 + tx;
   const int pix0 = (i0 + ty) * g.W + j;                       // pixel k lives 8*k rows further down
@@ -86,10 +85,10 @@ render_fwd_tiled(const T* __restrict__ x, const float* __restrict__ theta, T* __
       }
       continue;
     }
-    const T* img = xb + (long long)l * g.sl;
+    const SrcView sv_ = layer_view<T, kRagged>(x, g, src, b, l);
     if (mode == kStaged) {
       __syncthreads();                       // the previous layer's readers are done with buf
-      stage_footprint<T>(img, g, p, buf, tid);
+      stage_footprint<T>(g.m11 != 0, sv_, p, buf, tid);
       __syncthreads();
     }
     const float a01 = p.aff.a01, a11 = p.aff.a11;
@@ -106,7 +105,8 @@ render_fwd_tiled(const T* __restrict__ x, const float* __restrict__ theta, T* __
         upk(fma2(s.rg, zs2, zb2), r_, g_);
         upk(fma2(s.ba, zs2, zb2), b_, a);
       } else {
-        const float4 z = sample_pixel_direct<T>(img, p.aff, tx - kTW / 2, ty + kRowStep * k - kTH / 2, g.H, g.W, g.sh, g.sc,
+        const float4 z = sample_pixel_direct<T>(reinterpret_cast<const T*>(sv_.base), p.aff, tx - kTW / 2,
+                                                ty + kRowStep * k - kTH / 2, sv_.h, sv_.w, sv_.rowbytes / sizeof(T), sv_.plane / sizeof(T),
                                                 g.m11 ? 1.f : 0.f, g.m11 ? 0.5f : 1.f);
         r_ = z.x; g_ = z.y; b_ = z.z; a = z.w;
       }

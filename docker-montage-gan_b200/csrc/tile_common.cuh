@@ -42,10 +42,54 @@ struct LayerPlan {
   int pad_;
 };
 
+// One layer's pixels for the CTA's sample: SrcLayer with the batch offset applied and byte strides (they fit 32 bits,
+// host-checked).  Built from the kernel-parameter descriptors, so every field is CTA-uniform (uniform registers).
+struct SrcView {
+  const char* base;
+  unsigned plane, rowbytes;
+  int left, top, w, h;
+};
+// kRagged = false: the canvas layout, straight from the Geometry (compile-time zero offsets: the code the canvas path
+// always had); kRagged = true: from the per-layer descriptors.
+template <typename T, bool kRagged>
+__device__ __forceinline__ SrcView layer_view(const T* x, const Geometry& g, const SrcLayers& src, int b, int l) {
+  SrcView v;
+  if (kRagged) {
+    const SrcLayer& s = src.s[l];
+    v.base = reinterpret_cast<const char*>(reinterpret_cast<const T*>(s.ptr) + (long long)b * s.sb);
+    v.plane = (unsigned)s.sc * (unsigned)sizeof(T);
+    v.rowbytes = (unsigned)s.sh * (unsigned)sizeof(T);
+    v.left = s.left; v.top = s.top; v.w = s.w; v.h = s.h;
+  } else {
+    v.base = reinterpret_cast<const char*>(x + (long long)b * g.sb + (long long)l * g.sl);
+    v.plane = (unsigned)g.sc * (unsigned)sizeof(T);
+    v.rowbytes = (unsigned)g.sh * (unsigned)sizeof(T);
+    v.left = 0; v.top = 0; v.w = g.W; v.h = g.H;
+  }
+  return v;
+}
+template <typename T>
+__device__ __forceinline__ SrcView src_view(const SrcLayer& s, int b) {
+  SrcView v;
+  v.base = reinterpret_cast<const char*>(reinterpret_cast<const T*>(s.ptr) + (long long)b * s.sb);
+  v.plane = (unsigned)s.sc * (unsigned)sizeof(T);
+  v.rowbytes = (unsigned)s.sh * (unsigned)sizeof(T);
+  v.left = s.left; v.top = s.top; v.w = s.w; v.h = s.h;
+  return v;
+}
+
 // Plan one layer for the tile whose top-left pixel is (j0, i0).  Coordinates are carried relative
 // to the tile centre (|dj|, |di| <= 16) so that the fp32 per-pixel arithmetic stays accurate to
 // ~2e-6 px (the reference's own fp32 grid carries ~3e-5 px at 256x256).
-__device__ __forceinline__ LayerPlan plan_layer(const float* __restrict__ th, int H, int W, int j0, int i0, int vec) {
+struct SrcRect { int left, top, w, h; };
+template <bool kRagged>
+__device__ __forceinline__ SrcRect layer_rect(const Geometry& g, const SrcLayers& src, int l) {
+  if (kRagged) return SrcRect{src.s[l].left, src.s[l].top, src.s[l].w, src.s[l].h};
+  return SrcRect{0, 0, g.W, g.H};
+}
+
+__device__ __forceinline__ LayerPlan plan_layer(const float* __restrict__ th, int H, int W, int j0, int i0, int vec,
+                                                const SrcRect src) {
   LayerPlan p;
   p.aff = make_tile_affine(th, H, W, j0 + kTW / 2, i0 + kTH / 2);
   const TileAffine& t = p.aff;
@@ -61,16 +105,20 @@ __device__ __forceinline__ LayerPlan plan_layer(const float* __restrict__ th, in
   p.pad_ = 0;
   p.mode = kDirect;
   // NaN / huge placements take the bounds-checked direct path
+  // (the direct path addresses the layer's own pixels: origin moved to the rectangle's corner)
+  const int X0 = t.X0, Y0 = t.Y0;
+  p.aff.X0 = X0 - src.left; p.aff.Y0 = Y0 - src.top;
   if (!(fabsf(xmin) < 1.0e6f && fabsf(xmax) < 1.0e6f && fabsf(ymin) < 1.0e6f && fabsf(ymax) < 1.0e6f)) return p;
-  if (abs(t.X0) > (1 << 28) || abs(t.Y0) > (1 << 28)) return p;
-  int x_lo = t.X0 + (int)floorf(xmin), x_hi = t.X0 + (int)floorf(xmax) + 1;   // inclusive tap columns
-  int y_lo = t.Y0 + (int)floorf(ymin), y_hi = t.Y0 + (int)floorf(ymax) + 1;
-  if (x_hi < 0 || x_lo >= W || y_hi < 0 || y_lo >= H) { p.mode = kSkip; return p; }
+  if (abs(X0) > (1 << 28) || abs(Y0) > (1 << 28)) return p;
+  int x_lo = X0 + (int)floorf(xmin), x_hi = X0 + (int)floorf(xmax) + 1;   // inclusive tap columns
+  int y_lo = Y0 + (int)floorf(ymin), y_hi = Y0 + (int)floorf(ymax) + 1;
+  // the taps miss the layer's rectangle: a fully transparent layer for this tile
+  if (x_hi < src.left || x_lo >= src.left + src.w || y_hi < src.top || y_lo >= src.top + src.h) { p.mode = kSkip; return p; }
   x_lo &= ~(vec - 1);                                   // vec = staging vector width in texels (4 or 8)
   const int bw = (x_hi - x_lo + vec) & ~(vec - 1), bh = y_hi - y_lo + 1;
   p.x_lo = x_lo; p.y_lo = y_lo; p.bw = bw; p.bh = bh;
-  p.lrx = t.rx + (float)(t.X0 - x_lo);
-  p.lry = t.ry + (float)(t.Y0 - y_lo);
+  p.lrx = t.rx + (float)(X0 - x_lo);
+  p.lry = t.ry + (float)(Y0 - y_lo);
   p.mode = ((long long)bw * bh <= kCapTexels) ? kStaged : kDirect;
   return p;
 }
@@ -146,22 +194,21 @@ __device__ __forceinline__ void fill_store(uint2* dst, uint32_t o) {
 }
 
 template <typename T>
-__device__ __forceinline__ void stage_footprint(const T* __restrict__ img, const Geometry& g, const LayerPlan& p,
+__device__ __forceinline__ void stage_footprint(bool m11, const SrcView& sv, const LayerPlan& p,
                                                 typename Texel<T>::Vec* __restrict__ buf, int tid) {
   using Ld = typename std::conditional<sizeof(T) == 4, float4, uint2>::type;     // four texels of one channel
   constexpr int kIn = StageCfg<T>::kRowsInFlight;
   const int rsub = tid / kStageLanes, q = tid % kStageLanes;
   const int nv = p.bw / kStageVec;                            // vectors per footprint row
   typename std::conditional<sizeof(T) == 4, float, uint32_t>::type ob;
-  if constexpr (sizeof(T) == 4) ob = g.m11 ? -1.f : 0.f; else ob = Texel<T>::oob2(g.m11);
-  const char* base = reinterpret_cast<const char*>(img);
-  const unsigned plane = (unsigned)g.sc * (unsigned)sizeof(T);
-  const unsigned rowbytes = (unsigned)g.sh * (unsigned)sizeof(T);
+  if constexpr (sizeof(T) == 4) ob = m11 ? -1.f : 0.f; else ob = Texel<T>::oob2(m11);
+  const char* base = sv.base;
+  const unsigned plane = sv.plane, rowbytes = sv.rowbytes;
   for (int c0 = 0; c0 < nv; c0 += kStageLanes) {              // one pass unless the footprint is > 64 texels wide
     const int cv = c0 + q;
     const bool colv = cv < nv;
-    const int x = p.x_lo + kStageVec * cv;
-    const bool xin = colv && (unsigned)x < (unsigned)g.W;
+    const int x = p.x_lo + kStageVec * cv - sv.left;           // column inside the layer's rectangle
+    const bool xin = colv && (unsigned)x < (unsigned)sv.w;
     typename Texel<T>::Vec* dst = buf + rsub * p.bw + kStageVec * cv;
     const int dstep = kStageRows * p.bw;
     for (int r0 = rsub; r0 < p.bh; r0 += kStageRows * kIn) {
@@ -170,8 +217,8 @@ __device__ __forceinline__ void stage_footprint(const T* __restrict__ img, const
 #pragma unroll
       for (int it = 0; it < kIn; ++it) {
         const int r = r0 + it * kStageRows;
-        const int y = p.y_lo + r;
-        inside[it] = xin && r < p.bh && (unsigned)y < (unsigned)g.H;
+        const int y = p.y_lo + r - sv.top;
+        inside[it] = xin && r < p.bh && (unsigned)y < (unsigned)sv.h;
 #ifdef MGR_EXPERIMENT_NO_STAGE_LOADS
         inside[it] = false;
 #endif

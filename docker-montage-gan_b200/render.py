@@ -177,6 +177,104 @@ def alpha_composite_pytorch(blchw_lchw: torch.Tensor, use_premultiplied: bool = 
     return render(blchw_lchw, None, in_range="01")
 
 
+# --------------------------------------------------------------------------------------------------
+# ragged stacks: the local generators' outputs at native size, no padded canvas
+# --------------------------------------------------------------------------------------------------
+def _layer_array(tensors, canvas):
+    """ctypes MgrLayer[L] for [B,4,h,w] tensors centred on the canvas as pad_256 centres them
+    (custom_utils/image_utils.py:216-226: pad_x1 = pad_x // 2, the odd pixel goes right / down)."""
+    H, W = canvas
+    arr = (_lib.MgrLayer * len(tensors))()
+    for l, t in enumerate(tensors):
+        h, w = t.shape[2], t.shape[3]
+        arr[l] = _lib.MgrLayer(t.data_ptr(), t.stride(0), t.stride(1), t.stride(2), h, w, (H - h) // 2, (W - w) // 2)
+    return arr
+
+
+class _RenderRagged(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, theta, in_range, canvas, *layers):
+        lib = _lib.load()
+        H, W = canvas
+        L, B = len(layers), layers[0].shape[0]
+        dtype, device = layers[0].dtype, layers[0].device
+        xs = [t.detach() if t.stride(3) == 1 else t.detach().contiguous() for t in layers]
+        th = theta.detach().to(torch.float32).contiguous()
+        out = torch.empty((B, 4, H, W), dtype=dtype, device=device)
+        sav = None
+        if any(ctx.needs_input_grad):
+            sav = torch.empty(lib.mgr_saved_alpha_bytes(B, L, H, W, _DTYPES[dtype]), dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            rc = lib.mgr_render_forward_ragged(_layer_array(xs, canvas), _ptr(th), _ptr(out), _ptr(sav), B, L, H, W,
+                                               _DTYPES[dtype], _RANGES[in_range], _stream_ptr(device))
+        _lib.check(rc, "mgr_render_forward_ragged")
+        _lib.launch_count += 1
+        ctx.in_range, ctx.canvas, ctx.theta_dtype = in_range, canvas, theta.dtype
+        ctx.save_for_backward(th, out, sav, *xs)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        th, out, sav, *xs = ctx.saved_tensors
+        need_t = ctx.needs_input_grad[0]
+        need_x = any(ctx.needs_input_grad[3:])
+        if not (need_t or need_x):
+            return (None,) * (3 + len(xs))
+        if torch.is_grad_enabled() and grad_out.requires_grad:
+            raise NotImplementedError("double backward through the warp is not implemented")
+        lib = _lib.load()
+        H, W = ctx.canvas
+        L, B = len(xs), xs[0].shape[0]
+        dtype, device = xs[0].dtype, xs[0].device
+        flags = (_lib.MGR_NEED_GRAD_X if need_x else 0) | (_lib.MGR_NEED_GRAD_THETA if need_t else 0)
+        go = grad_out.detach().to(dtype).contiguous()
+        gxs = [torch.empty(t.shape, dtype=dtype, device=device) for t in xs] if need_x else None
+        gt = torch.empty((B, L, 2, 3), dtype=torch.float32, device=device) if need_t else None
+        ws_bytes = lib.mgr_render_backward_workspace_bytes(B, L, H, W, _lib.MGR_F32, 1, flags)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+        with torch.cuda.device(device):
+            rc = lib.mgr_render_backward_ragged(_layer_array(xs, ctx.canvas), _ptr(th), _ptr(out), _ptr(go), _ptr(sav),
+                                                _layer_array(gxs, ctx.canvas) if need_x else None, _ptr(gt), _ptr(ws), ws_bytes,
+                                                B, L, H, W, _DTYPES[dtype], _RANGES[ctx.in_range], flags, _stream_ptr(device))
+        _lib.check(rc, "mgr_render_backward_ragged")
+        _lib.launch_count += 1
+        if gt is not None and ctx.theta_dtype != torch.float32:
+            gt = gt.to(ctx.theta_dtype)
+        return (gt, None, None) + (tuple(gxs) if need_x else (None,) * L)
+
+
+def render_ragged(layers, theta: torch.Tensor, *, canvas=(256, 256), in_range: str = "m11") -> torch.Tensor:
+    """``render(make_batch_for_pos_estimator(layers, pad_value=-1, canvas), theta)`` without building the padded
+    ``[B,L,4,H,W]`` tensor: ``layers`` is the list of the L local generators' outputs ``[B,4,h_l,w_l]`` at their
+    native sizes (``training/dataset_aio.py:30-83``), each centred on the canvas the way ``pad_256`` does
+    (``custom_utils/image_utils.py:216-243``).  Pixels outside a layer read as the padding value (transparent black),
+    are never loaded, and get no gradient; tiles that miss a layer skip it.  Differentiable w.r.t. every layer and theta.
+
+    Layer widths and ``(W - w) // 2`` must be multiples of 4 (the reference's sizes are multiples of 32); otherwise
+    the library answers ``MGR_ERR_UNSUPPORTED`` -- build the canvas with ``make_batch_for_pos_estimator`` then.
+    """
+    layers = list(layers)
+    if len(layers) < 2:
+        raise ValueError("a ragged stack needs at least two layers")
+    B, H, W = layers[0].shape[0], canvas[0], canvas[1]
+    for t in layers:
+        if not isinstance(t, torch.Tensor) or t.dim() != 4 or t.shape[0] != B or t.shape[1] != 4:
+            raise ValueError("every layer must be a [B,4,h,w] tensor with the same B")
+        if t.dtype != layers[0].dtype or t.device != layers[0].device:
+            raise ValueError("layers must share dtype and device")
+        if t.shape[2] > H or t.shape[3] > W:
+            raise ValueError(f"layer {tuple(t.shape)} is larger than the canvas {canvas}")
+    if layers[0].dtype not in _DTYPES:
+        raise TypeError(f"dtype {layers[0].dtype} not supported (float32, bfloat16, float16)")
+    if in_range not in _RANGES:
+        raise ValueError(f"in_range must be 'm11' or '01', got {in_range!r}")
+    if tuple(theta.shape) != (B, len(layers), 2, 3):
+        raise ValueError(f"theta must be {(B, len(layers), 2, 3)}, got {tuple(theta.shape)}")
+    if not layers[0].is_cuda or theta.device != layers[0].device:
+        raise _lib.MontageRenderError("layers and theta must be CUDA tensors on one device: the renderer has no CPU path")
+    return _RenderRagged.apply(theta, in_range, (int(H), int(W)), *layers)
+
+
 def alpha_composite(blchw_lchw: torch.Tensor, *, in_range: str = "01", return_bytes: bool = False):
     """Drop-in for ``custom_utils.image_utils.alpha_composite`` (``image_utils.py:74-96``), the non-differentiable
     Pillow composite behind snapshots, metrics and the renderer-training targets: every layer is quantised to bytes

@@ -161,6 +161,32 @@ int mgr_composite_jvp(const void* x, const int64_t* x_strides, const void* tange
                       int B, int L, int H, int W, int dtype, int range_mode, void* stream);
 
 /*
+ * Ragged stacks: the L layers of a sample are separate tensors of their native sizes -- what
+ * the local generators emit (training/dataset_aio.py:30-83: 256x256, 160x224, 96x160, 64x96, ...) -- each centred
+ * on the H x W canvas, instead of one [B,L,4,H,W] tensor padded with -1 by make_batch_for_pos_estimator
+ * (custom_utils/image_utils.py:216-243).  Texels outside a layer's rectangle read as the padding value
+ * (transparent black), exactly as if the padded canvas had been built, but are never stored, loaded or
+ * differentiated; tiles whose taps miss the rectangle skip the layer.
+ *   layers[l]       layer l of every sample: ptr -> [B,4,h,w] (element strides sb, sc, sh; column stride 1) placed
+ *                   with its top-left texel at (left, top) of the canvas.  HOST array of L entries, read during the call.
+ *   grads[l]        where grad of layers[l] goes, same rectangle, written once (no zero-fill needed)
+ * Requirements (else MGR_ERR_UNSUPPORTED): theta given, 2 <= L <= 32, W, every w and every left multiples of 4,
+ * strides multiples of 4 elements (grads: 2), 4-element-aligned base pointers, rectangles inside the canvas.
+ * saved_alpha / workspace: as for mgr_render_forward / mgr_render_backward with the same B, L, H, W.
+ */
+typedef struct MgrLayer {
+  void* ptr;
+  int64_t sb, sc, sh;
+  int h, w, top, left;
+} MgrLayer;
+int mgr_render_forward_ragged(const MgrLayer* layers, const float* theta, void* out, void* saved_alpha,
+                              int B, int L, int H, int W, int dtype, int range_mode, void* stream);
+int mgr_render_backward_ragged(const MgrLayer* layers, const float* theta, const void* out, const void* grad_out,
+                               const void* saved_alpha, const MgrLayer* grads, float* grad_theta, void* workspace,
+                               size_t workspace_bytes, int B, int L, int H, int W, int dtype, int range_mode,
+                               int flags, void* stream);
+
+/*
  * Non-differentiable 8-bit composite, bit-exact with the reference's Pillow path
  * (custom_utils/image_utils.py:74-96 alpha_composite: ToPILImage -> Image.alpha_composite per layer -> ToTensor;
  * callers custom/loss_aio.py:351,362, custom/training_loop_aio.py:531,765,775, metrics/metric_utils.py:233,304).

@@ -565,3 +565,22 @@ def test_full_size_properties_config3_shard():
     out = mr.render(xo, tho)
     out.backward(go)
     assert xo.grad[:, :L - 1].abs().max().item() == 0.0 and (out[:, 3] == 1).all()
+
+
+def test_translation_backward_is_deterministic_with_global_gp():
+    """L = 9 at 256 x 256 fp32 no longer fits the (G_P, G_A) copy in shared memory, so the stencil backward keeps it in
+    the workspace, where the overlapping tiles all store their halo pixels: those stores must carry identical bits
+    (they once differed by an ulp between unrolled instances, making grad_x of the alpha plane vary run to run)."""
+    B, L, H, W = 2, 9, 256, 256
+    x = synth.make_layers(B, L, H, W, "S", seed=5).cuda()
+    th = _translation_theta(B, L, seed=5).cuda()
+    go = synth.make_grad_out(B, H, W, "randn", seed=5).cuda()
+
+    def run():
+        xr, tr = x.detach().requires_grad_(True), th.detach().requires_grad_(True)
+        out = mr.render(xr, tr)
+        return torch.autograd.grad(out, (xr, tr), go)[0]
+
+    g0 = run()
+    for _ in range(4):
+        assert torch.equal(run(), g0)
