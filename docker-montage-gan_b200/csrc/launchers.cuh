@@ -266,10 +266,11 @@ int launch_warp_backward(const void* x, const float* theta, const void* gout, vo
 template <typename T>
 int launch_pad_stack(const void* src, const long long* ss, void* dst, int B, int L, int l, int h, int w, int H, int W,
                      float pad, cudaStream_t s) {
-  const long long total = (long long)B * 4 * H * W;
-  const long long blocks = (total + 255) / 256;
-  pad_stack_kernel<T><<<(unsigned)(blocks < 148 * 32 ? blocks : 148 * 32), 256, 0, s>>>(
-      (const T*)src, ss[0], ss[1], ss[2], ss[3], (T*)dst, B, L, l, h, w, H, W, pad);
+  if ((long long)B * 4 > 65535 || (H + 3) / 4 > 65535) return fail(MGR_ERR_UNSUPPORTED, "pad_stack: B=%d or H=%d too large for one call", B, H);
+  dim3 grid((W + 255) / 256, (H + 3) / 4, B * 4);
+  const bool vec = W % 4 == 0 && reinterpret_cast<uintptr_t>(dst) % (4 * sizeof(T)) == 0;
+  if (vec) pad_stack_kernel<T, true><<<grid, 256, 0, s>>>((const T*)src, ss[0], ss[1], ss[2], ss[3], (T*)dst, L, l, h, w, H, W, pad);
+  else pad_stack_kernel<T, false><<<grid, 256, 0, s>>>((const T*)src, ss[0], ss[1], ss[2], ss[3], (T*)dst, L, l, h, w, H, W, pad);
   MGR_CUDA(cudaGetLastError());
   count_launch();
   return MGR_OK;

@@ -110,20 +110,35 @@ static __global__ void translation_to_theta_kernel(const float* __restrict__ tr,
 }
 
 // ---- centre-pad one layer's generator output [B,4,h,w] into the canvas dst[:, l] of [B,L,4,H,W] ----
-template <typename T>
-__global__ void pad_stack_kernel(const T* __restrict__ src, long long ssb, long long ssc, long long ssh, long long ssw,
-                                 T* __restrict__ dst, int B, int L, int l, int h, int w, int H, int W, float pad) {
+// Grid (ceil(W / 256), ceil(H / 4), B * 4): a thread owns four adjacent canvas pixels of one row (no divisions;
+// one 8- / 16-byte store when kVec4, i.e. W % 4 == 0 and an aligned dst).
+template <typename T, bool kVec4>
+__global__ void __launch_bounds__(256)
+pad_stack_kernel(const T* __restrict__ src, long long ssb, long long ssc, long long ssh, long long ssw,
+                 T* __restrict__ dst, int L, int l, int h, int w, int H, int W, float pad) {
   const int top = (H - h) / 2, left = (W - w) / 2;            // pad_256: pad_x1 = pad_x // 2 (image_utils.py:222-225)
-  const long long total = (long long)B * 4 * H * W;
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
-    const int X = (int)(k % W);
-    const int Y = (int)((k / W) % H);
-    const int c = (int)((k / ((long long)W * H)) % 4);
-    const int b = (int)(k / ((long long)W * H * 4));
-    const int y = Y - top, xx = X - left;
-    T* q = dst + ((((long long)b * L + l) * 4 + c) * H + Y) * W + X;
-    if ((unsigned)y < (unsigned)h && (unsigned)xx < (unsigned)w) *q = src[b * ssb + c * ssc + y * ssh + xx * ssw];
-    else st(q, pad);
+  const int X0 = 4 * (blockIdx.x * 64 + (threadIdx.x & 63)), Y = blockIdx.y * 4 + (threadIdx.x >> 6);
+  const int b = blockIdx.z >> 2, c = blockIdx.z & 3;
+  if (X0 >= W || Y >= H) return;
+  const int y = Y - top;
+  const bool yin = (unsigned)y < (unsigned)h;
+  const T* srow = src + b * ssb + c * ssc + (long long)y * ssh;
+  __align__(16) T v[4];
+  T padv;
+  st(&padv, pad);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int xx = X0 + q - left;
+    v[q] = (yin && (unsigned)xx < (unsigned)w) ? srow[xx * ssw] : padv;
+  }
+  T* q0 = dst + ((((long long)b * L + l) * 4 + c) * H + Y) * W + X0;
+  if (kVec4) {
+    if constexpr (sizeof(T) == 4) *reinterpret_cast<float4*>(q0) = *reinterpret_cast<const float4*>(v);
+    else *reinterpret_cast<uint2*>(q0) = *reinterpret_cast<const uint2*>(v);
+  } else {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (X0 + q < W) q0[q] = v[q];
   }
 }
 
