@@ -143,3 +143,25 @@ def test_ragged_argument_rules():
         mr.render_ragged([good[0], torch.zeros(2, 4, 80, 16, device="cuda")], theta, canvas=canvas)     # taller than the canvas
     with pytest.raises(_lib.MontageRenderError):
         mr.render_ragged([t.cpu() for t in good], theta.cpu(), canvas=canvas)                            # no CPU path
+
+
+def test_ragged_layers_may_be_views_into_a_padded_canvas():
+    """A caller that already holds the padded [B,L,4,H,W] tensor (the STN's localisation CNN reads it) can still tell
+    the renderer where each layer's content is: strided views of the canvas are valid ragged layers, nothing is copied."""
+    canvas, sizes = (128, 128), [(128, 128), (64, 96), (32, 48), (17, 64)]
+    B, L = 2, len(sizes)
+    _, padded = _make(B, canvas, sizes, "S", seed=13)
+    theta = synth.make_theta(B, L, "I", seed=13)
+    go = synth.make_grad_out(B, 128, 128, "randn", seed=13)
+    xp = padded.cuda()
+    views = [xp[:, l, :, (128 - h) // 2:(128 - h) // 2 + h, (128 - w) // 2:(128 - w) // 2 + w].requires_grad_(True)
+             for l, (h, w) in enumerate(sizes)]
+    assert not views[1].is_contiguous()
+    th = theta.cuda().requires_grad_(True)
+    out = mr.render_ragged(views, th, canvas=canvas)
+    grads = torch.autograd.grad(out, views + [th], go.cuda())
+    out_c, gx_c, gt_c = _run_canvas(padded, theta, go)
+    assert torch.equal(out.detach().cpu(), out_c)
+    for g, gc in zip(grads[:-1], _crop(gx_c, sizes, canvas)):
+        assert g.is_contiguous() and torch.equal(g.cpu(), gc)
+    assert rel_err(grads[-1].cpu().numpy(), gt_c.numpy()) < 1e-5
