@@ -148,8 +148,10 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
   if (nt) MGR_CUDA(cudaMemsetAsync(gtheta, 0, sizeof(float) * 6 * g.B * g.L, s));
   size_t smem = align16(tiled_smem_bytes(g.L, sizeof(Vec))) +
                 sizeof(float) * (size_t)g.L * kPx * kTiledThreads;                // + transmittance stash
-  const size_t gp_bytes = sizeof(float4) * kPx * kTiledThreads;                   // (G_P, G_A) copy, if 3 CTAs/SM still fit
-  const bool gp_smem = (smem + gp_bytes) * 3 + 3 * 1024 <= 227 * 1024;
+  // (G_P, G_A) copy in shared memory if two CTAs per SM still fit (the kernels are compiled for two: at three they
+  // spill, and the spills cost more than the third CTA hides)
+  const size_t gp_bytes = sizeof(float4) * kPx * kTiledThreads;
+  const bool gp_smem = (smem + gp_bytes) * 2 + 2 * 1024 <= 227 * 1024;
   if (gp_smem) smem += gp_bytes;
   dim3 grid((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B);
   const int shift = debug_path() != 2;
@@ -180,7 +182,7 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
   }
   if (shift) {
     size_t smem3 = shift_bwd_smem_bytes(g.L, sizeof(Vec));
-    const bool gp_smem3 = (smem3 + gp_bytes) * 3 + 3 * 1024 <= 227 * 1024;
+    const bool gp_smem3 = (smem3 + gp_bytes) * 2 + 2 * 1024 <= 227 * 1024;
     if (gp_smem3) smem3 += gp_bytes;
     dim3 grid3((g.W + 1 + kAnchor - 1) / kAnchor, (g.H + 1 + kAnchor - 1) / kAnchor, g.B);
     auto launch3 = [&](auto kern) -> int {

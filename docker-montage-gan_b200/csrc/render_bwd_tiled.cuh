@@ -29,8 +29,11 @@ namespace mgr {
 //   rec [B*L][H*W] float2 = (T_l a_l, d a_l)        gp [B][H*W] float4 = (G_P.rgb, G_A)
 //   inverse plans [B*L] InverseLayer (128 B each)        order [B*L] int + 2 counters
 
+#ifndef MGR_P1_BLOCKS
+#define MGR_P1_BLOCKS 2
+#endif
 template <typename T, bool kNeedTheta, bool kGPSmem, bool kRagged>
-__global__ void __launch_bounds__(kTiledThreads, kGPSmem ? 3 : 2)
+__global__ void __launch_bounds__(kTiledThreads, kGPSmem ? MGR_P1_BLOCKS : 2)
 render_bwd_pass1(const T* __restrict__ x, const __grid_constant__ SrcLayers src, const float* __restrict__ theta, const T* __restrict__ out,
                  const T* __restrict__ gout, const typename SavedAlpha<T>::type* __restrict__ sav,
                  float2* __restrict__ rec, float4* __restrict__ gp, float* __restrict__ gtheta, Geometry g,
@@ -43,7 +46,7 @@ render_bwd_pass1(const T* __restrict__ x, const __grid_constant__ SrcLayers src,
   // [L][kPx][256]: transmittance in front of layer l, later the layer's theta-gradient partials (16-byte aligned)
   float* stash = reinterpret_cast<float*>(smem_raw + align16(sizeof(Vec) * kCapTexels + sizeof(LayerPlan) * g.L));
   float* Tst = stash + tid;
-  // (G_P, G_A) per pixel: a shared-memory copy when it still leaves room for 3 CTAs/SM (host decides), else the
+  // (G_P, G_A) per pixel: a shared-memory copy when it still leaves room for 2 CTAs/SM (host decides), else the
   // thread re-reads its own entries of the global gp buffer (L1/L2 hits)
   float4* GPs = reinterpret_cast<float4*>(stash + (size_t)g.L * kPx * kTiledThreads) + tid;   // [kPx][256]
   const int b = blockIdx.z;
@@ -315,8 +318,11 @@ template <> struct Pack2<__half> {
 
 __device__ __forceinline__ float hat(float u) { return fmaxf(1.f - fabsf(u), 0.f); }
 
+#ifndef MGR_P2_BLOCKS
+#define MGR_P2_BLOCKS 4
+#endif
 template <typename T, bool kRagged>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, MGR_P2_BLOCKS)
 render_bwd_pass2(const InverseLayer* __restrict__ plans, const int* __restrict__ order, const float2* __restrict__ rec,
                  const float4* __restrict__ gp, T* __restrict__ gx, const __grid_constant__ DstLayers dst, Geometry g,
                  int skip_shift) {

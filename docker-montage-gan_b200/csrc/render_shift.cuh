@@ -21,6 +21,14 @@
 #pragma once
 #include "render_tiled.cuh"
 
+// resident CTAs per SM the stencil kernels are compiled for (developer knobs, tools/ab.py)
+#ifndef MGR_SHB_BLOCKS
+#define MGR_SHB_BLOCKS 2
+#endif
+#ifndef MGR_SHF_BLOCKS
+#define MGR_SHF_BLOCKS 3
+#endif
+
 namespace mgr {
 
 struct ShiftPlan {     // 16 bytes: arrays behind a ShiftPlan[L] stay 16-byte aligned
@@ -57,7 +65,7 @@ constexpr int kShiftCap = (kTW + 2 * kStageVec) * (kTH + 1);        // staged te
 // forward
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool kSave>
-__global__ void __launch_bounds__(kTiledThreads, 3)
+__global__ void __launch_bounds__(kTiledThreads, MGR_SHF_BLOCKS)
 render_fwd_shift(const __grid_constant__ SrcLayers src, const float* __restrict__ theta, T* __restrict__ out,
                  typename SavedAlpha<T>::type* __restrict__ sav, Geometry g) {
   using Vec = typename Texel<T>::Vec;
@@ -153,7 +161,7 @@ inline size_t shift_fwd_smem_bytes(int L, size_t vec_bytes) { return vec_bytes *
 constexpr int kAnchor = kTW - 1;
 
 template <typename T, bool kNeedX, bool kNeedTheta, bool kGPSmem>
-__global__ void __launch_bounds__(kTiledThreads, kGPSmem ? 3 : 2)
+__global__ void __launch_bounds__(kTiledThreads, kGPSmem ? MGR_SHB_BLOCKS : 2)
 render_bwd_shift(const __grid_constant__ SrcLayers src, const float* __restrict__ theta, const T* __restrict__ out,
                  const T* __restrict__ gout, const typename SavedAlpha<T>::type* __restrict__ sav,
                  const __grid_constant__ DstLayers dst, float* __restrict__ gtheta, float4* __restrict__ gp, Geometry g) {

@@ -41,8 +41,11 @@ __device__ __noinline__ float4 sample_pixel_direct(const T* __restrict__ img, co
 
 // L >= 2 only (a single layer is returned untouched by the reference; the host routes L == 1 to
 // the direct kernel).  kSave: also write the sampled alpha of every (layer, pixel) to `sav`.
+#ifndef MGR_FWD_BLOCKS
+#define MGR_FWD_BLOCKS 3
+#endif
 template <typename T, bool kSave, bool kRagged>
-__global__ void __launch_bounds__(kTiledThreads, 3)
+__global__ void __launch_bounds__(kTiledThreads, MGR_FWD_BLOCKS)
 render_fwd_tiled(const T* __restrict__ x, const __grid_constant__ SrcLayers src, const float* __restrict__ theta, T* __restrict__ out,
                  typename SavedAlpha<T>::type* __restrict__ sav, Geometry g, int skip_shift) {
   using Vec = typename Texel<T>::Vec;
