@@ -105,8 +105,7 @@ render_fwd_shift(const __grid_constant__ SrcLayers src, const float* __restrict_
       }
       continue;
     }
-    __syncthreads();
-    stage_footprint<T>(g.m11 != 0, src_view<T>(src.s[l], b), p, buf, tid);
+    stage_footprint<T, true>(g.m11 != 0, src_view<T>(src.s[l], b), p, buf, tid);   // takes the "readers are done" barrier with its loads in flight
     __syncthreads();
     const f32x2 fx2 = bc(sp.fx), fy2 = bc(sp.fy);
     const Vec* q = buf + (kPx * ty) * p.bw + (tx + j0 + sp.X - p.x_lo);

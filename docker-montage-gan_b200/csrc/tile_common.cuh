@@ -193,10 +193,14 @@ __device__ __forceinline__ void fill_store(uint2* dst, uint32_t o) {
   d[0] = v; d[1] = v;
 }
 
-template <typename T>
+// kBarrier: the caller's "previous readers are done with buf" barrier is taken INSIDE, after the loads of the first
+// block of rows have been issued and before the first shared store -- warps that reach the barrier early wait with
+// their global loads already in flight (one barrier per layer then hides part of the staging latency for free).
+template <typename T, bool kBarrier = false>
 __device__ __forceinline__ void stage_footprint(bool m11, const SrcView& sv, const LayerPlan& p,
                                                 typename Texel<T>::Vec* __restrict__ buf, int tid) {
   using Ld = typename std::conditional<sizeof(T) == 4, float4, uint2>::type;     // four texels of one channel
+  using Vec = typename Texel<T>::Vec;
   constexpr int kIn = StageCfg<T>::kRowsInFlight;
   const int rsub = tid / kStageLanes, q = tid % kStageLanes;
   const int nv = p.bw / kStageVec;                            // vectors per footprint row
@@ -204,38 +208,51 @@ __device__ __forceinline__ void stage_footprint(bool m11, const SrcView& sv, con
   if constexpr (sizeof(T) == 4) ob = m11 ? -1.f : 0.f; else ob = Texel<T>::oob2(m11);
   const char* base = sv.base;
   const unsigned plane = sv.plane, rowbytes = sv.rowbytes;
-  for (int c0 = 0; c0 < nv; c0 += kStageLanes) {              // one pass unless the footprint is > 64 texels wide
-    const int cv = c0 + q;
-    const bool colv = cv < nv;
+  const int dstep = kStageRows * p.bw;
+  Ld R[kIn], G[kIn], Bl[kIn], A[kIn];
+  bool inside[kIn];
+  // rows r0, r0 + kStageRows, ... of vector column cv: issue the loads
+  auto load_block = [&](int cv, int r0) {
     const int x = p.x_lo + kStageVec * cv - sv.left;           // column inside the layer's rectangle
-    const bool xin = colv && (unsigned)x < (unsigned)sv.w;
-    typename Texel<T>::Vec* dst = buf + rsub * p.bw + kStageVec * cv;
-    const int dstep = kStageRows * p.bw;
-    for (int r0 = rsub; r0 < p.bh; r0 += kStageRows * kIn) {
-      Ld R[kIn], G[kIn], Bl[kIn], A[kIn];
-      bool inside[kIn];
+    const bool xin = cv < nv && (unsigned)x < (unsigned)sv.w;
 #pragma unroll
-      for (int it = 0; it < kIn; ++it) {
-        const int r = r0 + it * kStageRows;
-        const int y = p.y_lo + r - sv.top;
-        inside[it] = xin && r < p.bh && (unsigned)y < (unsigned)sv.h;
+    for (int it = 0; it < kIn; ++it) {
+      const int r = r0 + it * kStageRows;
+      const int y = p.y_lo + r - sv.top;
+      inside[it] = xin && r < p.bh && (unsigned)y < (unsigned)sv.h;
 #ifdef MGR_EXPERIMENT_NO_STAGE_LOADS
-        inside[it] = false;
+      inside[it] = false;
 #endif
-        if (inside[it]) {
-          const unsigned off = (unsigned)y * rowbytes + (unsigned)x * (unsigned)sizeof(T);
-          R[it] = __ldg(reinterpret_cast<const Ld*>(base + off));
-          G[it] = __ldg(reinterpret_cast<const Ld*>(base + (off + plane)));
-          Bl[it] = __ldg(reinterpret_cast<const Ld*>(base + (off + 2 * plane)));
-          A[it] = __ldg(reinterpret_cast<const Ld*>(base + (off + 3 * plane)));
-        }
+      if (inside[it]) {
+        const unsigned off = (unsigned)y * rowbytes + (unsigned)x * (unsigned)sizeof(T);
+        R[it] = __ldg(reinterpret_cast<const Ld*>(base + off));
+        G[it] = __ldg(reinterpret_cast<const Ld*>(base + (off + plane)));
+        Bl[it] = __ldg(reinterpret_cast<const Ld*>(base + (off + 2 * plane)));
+        A[it] = __ldg(reinterpret_cast<const Ld*>(base + (off + 3 * plane)));
       }
+    }
+  };
+  // ... and interleave them into shared memory (texels outside the layer: the padding value)
+  auto store_block = [&](int cv, int r0) {
+    Vec* dst = buf + r0 * p.bw + kStageVec * cv;
 #pragma unroll
-      for (int it = 0; it < kIn; ++it) {
-        if (inside[it]) interleave_store(dst, R[it], G[it], Bl[it], A[it]);
-        else if (colv && r0 + it * kStageRows < p.bh) fill_store(dst, ob);     // outside the image
-        dst += dstep;
-      }
+    for (int it = 0; it < kIn; ++it) {
+      if (inside[it]) interleave_store(dst, R[it], G[it], Bl[it], A[it]);
+      else if (cv < nv && r0 + it * kStageRows < p.bh) fill_store(dst, ob);
+      dst += dstep;
+    }
+  };
+  int first_r0 = rsub;
+  if (kBarrier) {                                             // peeled first block: every thread takes the barrier
+    load_block(q, rsub);
+    __syncthreads();
+    store_block(q, rsub);
+    first_r0 = rsub + kStageRows * kIn;
+  }
+  for (int c0 = 0; c0 < nv; c0 += kStageLanes) {              // one pass unless the footprint is > 64 texels wide
+    for (int r0 = (c0 == 0 ? first_r0 : rsub); r0 < p.bh; r0 += kStageRows * kIn) {
+      load_block(c0 + q, r0);
+      store_block(c0 + q, r0);
     }
   }
 }
