@@ -144,8 +144,19 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
   float2* rec = reinterpret_cast<float2*>(ws);
   float4* gp = reinterpret_cast<float4*>(reinterpret_cast<char*>(ws) + sizeof(float2) * (size_t)g.B * g.L * g.H * g.W);
   InverseLayer* inv = reinterpret_cast<InverseLayer*>(reinterpret_cast<char*>(gp) + sizeof(float4) * (size_t)g.B * g.H * g.W);
-  int* order = reinterpret_cast<int*>(inv + (size_t)g.B * g.L);          // [B*L] + 2 counters
+  int* order = reinterpret_cast<int*>(inv + (size_t)g.B * g.L);          // [B*L] + 2 counters, then work [B*L] + 2 counters
+  int* work = order + (size_t)g.B * g.L + 2;
+  int* wcnt = work + (size_t)g.B * g.L;                                  // [0] layers in the work list
+  int* sflag = wcnt + 2;                                                 // [B] sample is all translations
+  if ((long long)g.B * g.L > 65535) return fail(MGR_ERR_UNSUPPORTED, "B*L=%lld exceeds 65535 per backward call; split the batch", (long long)g.B * g.L);
   if (nt) MGR_CUDA(cudaMemsetAsync(gtheta, 0, sizeof(float) * 6 * g.B * g.L, s));
+  // placements first: inverse plans + launch order for pass 2, and the per-sample "all translations" flags every
+  // kernel below uses to claim or decline a sample with one load
+  MGR_CUDA(cudaMemsetAsync(order + g.B * g.L, 0, 2 * sizeof(int), s));
+  inverse_plans_kernel<<<(g.B * g.L + 127) / 128, 128, 0, s>>>(theta, inv, g.B * g.L, g.H, g.W, order, order + g.B * g.L);
+  sample_flags_kernel<<<1, 256, 0, s>>>(inv, g.B, g.L, order, work, wcnt, sflag, debug_path() != 2);
+  MGR_CUDA(cudaGetLastError());
+  count_launch(2);
   size_t smem = align16(tiled_smem_bytes(g.L, sizeof(Vec))) +
                 sizeof(float) * (size_t)g.L * kPx * kTiledThreads;                // + transmittance stash
   // (G_P, G_A) copy in shared memory if two CTAs per SM still fit (the kernels are compiled for two: at three they
@@ -159,7 +170,7 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
     auto launch = [&](auto kern) -> int {
       MGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       kern<<<grid, kTiledThreads, smem, s>>>((const T*)x, src, theta, (const T*)out, (const T*)gout, (const SA*)sav, rec, gp,
-                                             nt ? gtheta : nullptr, g, shift);
+                                             nt ? gtheta : nullptr, g, sflag, shift);
       return MGR_OK;
     };
     int rc;
@@ -171,12 +182,7 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
   count_launch();
   if (nx) {
     dim3 grid2((g.W + kP2W - 1) / kP2W, (g.H + kP2H - 1) / kP2H, g.B * g.L);
-    MGR_CUDA(cudaMemsetAsync(order + g.B * g.L, 0, 2 * sizeof(int), s));
-    inverse_plans_kernel<<<(g.B * g.L + 127) / 128, 128, 0, s>>>(theta, inv, g.B * g.L, g.H, g.W, order, order + g.B * g.L);
-    sample_flags_kernel<<<(g.B + 127) / 128, 128, 0, s>>>(inv, g.B, g.L);
-    MGR_CUDA(cudaGetLastError());
-    count_launch(2);
-    render_bwd_pass2<T, kRagged><<<grid2, 256, 0, s>>>(inv, order, rec, gp, (T*)gx, dst, g, shift);
+    render_bwd_pass2<T, kRagged><<<grid2, 256, 0, s>>>(inv, work, wcnt, rec, gp, (T*)gx, dst, g);
     MGR_CUDA(cudaGetLastError());
     count_launch();
   }
@@ -188,7 +194,7 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
     auto launch3 = [&](auto kern) -> int {
       MGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       kern<<<grid3, kTiledThreads, smem3, s>>>(src, theta, (const T*)out, (const T*)gout, (const SA*)sav, dst,
-                                               nt ? gtheta : nullptr, gp, g);
+                                               nt ? gtheta : nullptr, gp, g, sflag);
       return MGR_OK;
     };
     int rc;

@@ -106,7 +106,8 @@ int mgr_render_forward(const void* x, const int64_t* x_strides, const float* the
 size_t mgr_render_backward_workspace_bytes(int B, int L, int H, int W, int dtype, int has_theta, int flags) {
   if (B <= 0 || L <= 0 || H <= 0 || W <= 0 || !has_theta) return 0;
   // tiled two-pass path: fp32 records (T_l a_l, d a_l) per layer-pixel + G_P per pixel
-  size_t need = ((size_t)B * L * H * W) * 8 + ((size_t)B * H * W) * 16 + (size_t)B * L * (128 + 4) + 16;
+  // + per layer: inverse plan (128 B), launch-order entry, work-list entry; + 4 counters; + a flag per sample
+  size_t need = ((size_t)B * L * H * W) * 8 + ((size_t)B * H * W) * 16 + (size_t)B * L * (128 + 4 + 4) + 32 + (size_t)B * 4;
   // general direct-gather path with 16-bit storage: fp32 scatter accumulator
   if ((flags & MGR_NEED_GRAD_X) && dtype != MGR_F32) {
     const size_t scatter = sizeof(float) * (size_t)B * L * 4 * H * W;

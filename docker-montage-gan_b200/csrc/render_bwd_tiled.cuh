@@ -28,6 +28,7 @@ namespace mgr {
 // workspace layout of the tiled backward (all fp32):
 //   rec [B*L][H*W] float2 = (T_l a_l, d a_l)        gp [B][H*W] float4 = (G_P.rgb, G_A)
 //   inverse plans [B*L] InverseLayer (128 B each)        order [B*L] int + 2 counters
+//   work [B*L] int + 2 counters (pass 2's compact layer list)   sample_all_shift [B] int
 
 #ifndef MGR_P1_BLOCKS
 #define MGR_P1_BLOCKS 2
@@ -37,7 +38,7 @@ __global__ void __launch_bounds__(kTiledThreads, kGPSmem ? MGR_P1_BLOCKS : 2)
 render_bwd_pass1(const T* __restrict__ x, const __grid_constant__ SrcLayers src, const float* __restrict__ theta, const T* __restrict__ out,
                  const T* __restrict__ gout, const typename SavedAlpha<T>::type* __restrict__ sav,
                  float2* __restrict__ rec, float4* __restrict__ gp, float* __restrict__ gtheta, Geometry g,
-                 int skip_shift) {
+                 const int* __restrict__ sample_all_shift, int skip_shift) {
   using Vec = typename Texel<T>::Vec;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Vec* buf = reinterpret_cast<Vec*>(smem_raw);                                            // [kCapTexels]
@@ -50,7 +51,7 @@ render_bwd_pass1(const T* __restrict__ x, const __grid_constant__ SrcLayers src,
   // thread re-reads its own entries of the global gp buffer (L1/L2 hits)
   float4* GPs = reinterpret_cast<float4*>(stash + (size_t)g.L * kPx * kTiledThreads) + tid;   // [kPx][256]
   const int b = blockIdx.z;
-  if (skip_shift && cta_all_shift(theta + (long long)b * g.L * 6, g.L, tid, kTiledThreads)) return;   // render_bwd_shift's
+  if (skip_shift && sample_all_shift[b]) return;            // render_bwd_shift's sample (flag from sample_flags_kernel)
   const int j0 = blockIdx.x * kTW, i0 = blockIdx.y * kTH;
   const int tx = tid & 31, ty = tid >> 5;
   for (int l = tid; l < g.L; l += kTiledThreads)
@@ -291,13 +292,43 @@ static __global__ void inverse_plans_kernel(const float* __restrict__ theta, Inv
   plans[k] = q;
 }
 
-// one thread per sample: are all of its layers pure translations?  (those samples belong to render_bwd_shift)
-static __global__ void sample_flags_kernel(InverseLayer* __restrict__ plans, int B, int L) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  int all = 1;
-  for (int l = 0; l < L; ++l) all &= plans[b * L + l].shift_only;
-  for (int l = 0; l < L; ++l) plans[b * L + l].all_shift = all;
+// One CTA.  Phase 1, a thread per sample: are all of its layers pure translations?  (those samples belong to
+// render_bwd_shift).  Phase 2: the layers pass 2 has to process, in launch order (order[] minus the layers of
+// all-translation samples when the stencil kernels are on), compacted into work[0 .. wcnt[0]).  A batch of
+// translations leaves pass 2 with nothing to do.
+static __global__ void __launch_bounds__(256)
+sample_flags_kernel(InverseLayer* __restrict__ plans, int B, int L, const int* __restrict__ order, int* __restrict__ work,
+                    int* __restrict__ wcnt, int* __restrict__ sample_all_shift, int skip_shift) {
+  __shared__ int s_warp[8], s_base;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int b = tid; b < B; b += 256) {
+    int all = 1;
+    for (int l = 0; l < L; ++l) all &= plans[b * L + l].shift_only;
+    for (int l = 0; l < L; ++l) plans[b * L + l].all_shift = all;
+    sample_all_shift[b] = all;                  // what pass 1 and the stencil backward read to claim / decline a sample
+  }
+  if (tid == 0) s_base = 0;
+  __syncthreads();                              // flags visible to the whole CTA
+  const int n = B * L;
+  for (int start = 0; start < n; start += 256) {
+    const int i = start + tid;
+    const int layer = i < n ? order[i] : 0;
+    const bool keep = i < n && !(skip_shift && plans[layer].all_shift);
+    const unsigned m = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[wid] = __popc(m);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < wid; ++w) off += s_warp[w];
+    if (keep) work[off + __popc(m & ((1u << lane) - 1u))] = layer;
+    __syncthreads();
+    if (tid == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) tot += s_warp[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  if (tid == 0) { wcnt[0] = s_base; wcnt[1] = 0; }
 }
 
 // Block of 256 threads = 32 x 8 threads, each owning a 2 x 2 block of texels -> 64 x 16 texels per CTA.
@@ -327,19 +358,16 @@ __device__ __forceinline__ float hat(float u) { return fmaxf(1.f - fabsf(u), 0.f
 #ifndef MGR_P2_BLOCKS
 #define MGR_P2_BLOCKS 4
 #endif
+// one 64 x 16 texel block of layer n = b * L + l
 template <typename T, bool kRagged>
-__global__ void __launch_bounds__(256, MGR_P2_BLOCKS)
-render_bwd_pass2(const InverseLayer* __restrict__ plans, const int* __restrict__ order, const float2* __restrict__ rec,
-                 const float4* __restrict__ gp, T* __restrict__ gx, const __grid_constant__ DstLayers dst, Geometry g,
-                 int skip_shift) {
+__device__ __forceinline__ void pass2_block(const InverseLayer* __restrict__ plans, int n, int x0b, int y0b,
+                                            const float2* __restrict__ rec, const float4* __restrict__ gp, T* __restrict__ gx,
+                                            const DstLayers& dst, const Geometry& g) {
   __shared__ float s_jcf, s_icf;
   __shared__ int s_JC, s_IC, s_ok;
-  const int n = order[blockIdx.z];              // b * L + l, heavy layers first
   const int b = n / g.L;
-  const int x0b = blockIdx.x * kP2W, y0b = blockIdx.y * kP2H;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const InverseLayer& L_ = plans[n];
-  if (skip_shift && L_.all_shift) return;      // all-translation samples are written by render_bwd_shift
   const int hw = g.H * g.W;
   const int x = x0b + 2 * tx, y = y0b + 2 * ty;                // top-left texel of this thread's 2 x 2 block (canvas coordinates)
   const float zs = g.m11 ? 0.5f : 1.f;          // d z / d x_texel = zs * weight
@@ -534,6 +562,18 @@ render_bwd_pass2(const InverseLayer* __restrict__ plans, const int* __restrict__
     Pack2<T>::store(o + 2 * dl.sc, zs * b0, zs * b1);
     Pack2<T>::store(o + 3 * dl.sc, zs * a0, zs * a1);
   }
+}
+
+// One CTA per (layer of the work list, 64 x 16 texel block).  The grid's z extent is B * L (the host cannot know how
+// many layers the work list holds); CTAs beyond wcnt[0] leave after that one load -- for a batch of translations that
+// is all of them.  (Walking the items inside persistent or grid-stride CTAs was measured 3-8 % slower on general batches.)
+template <typename T, bool kRagged>
+__global__ void __launch_bounds__(256, MGR_P2_BLOCKS)
+render_bwd_pass2(const InverseLayer* __restrict__ plans, const int* __restrict__ work, const int* __restrict__ wcnt,
+                 const float2* __restrict__ rec, const float4* __restrict__ gp, T* __restrict__ gx,
+                 const __grid_constant__ DstLayers dst, Geometry g) {
+  if ((int)blockIdx.z >= wcnt[0]) return;
+  pass2_block<T, kRagged>(plans, work[blockIdx.z], blockIdx.x * kP2W, blockIdx.y * kP2H, rec, gp, gx, dst, g);
 }
 
 }  // namespace mgr

@@ -163,7 +163,8 @@ template <typename T, bool kNeedX, bool kNeedTheta, bool kGPSmem>
 __global__ void __launch_bounds__(kTiledThreads, kGPSmem ? MGR_SHB_BLOCKS : 2)
 render_bwd_shift(const __grid_constant__ SrcLayers src, const float* __restrict__ theta, const T* __restrict__ out,
                  const T* __restrict__ gout, const typename SavedAlpha<T>::type* __restrict__ sav,
-                 const __grid_constant__ DstLayers dst, float* __restrict__ gtheta, float4* __restrict__ gp, Geometry g) {
+                 const __grid_constant__ DstLayers dst, float* __restrict__ gtheta, float4* __restrict__ gp, Geometry g,
+                 const int* __restrict__ sample_all_shift) {
   using Vec = typename Texel<T>::Vec;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Vec* buf = reinterpret_cast<Vec*>(smem_raw);                                           // [kShiftCap]
@@ -174,7 +175,7 @@ render_bwd_shift(const __grid_constant__ SrcLayers src, const float* __restrict_
   float* Tst = stash + tid;
   const int b = blockIdx.z;
   const float* thb = theta + (long long)b * g.L * 6;
-  if (!cta_all_shift(thb, g.L, tid, kTiledThreads)) return;
+  if (!sample_all_shift[b]) return;                           // per-sample flag from sample_flags_kernel
   // pixel tile: origin one pixel left/up of the anchors it owns; neighbouring tiles overlap by one pixel
   const int j0 = blockIdx.x * kAnchor - 1, i0 = blockIdx.y * kAnchor - 1;
   const int tx = tid & 31, ty = tid >> 5;
