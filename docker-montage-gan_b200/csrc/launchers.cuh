@@ -5,6 +5,7 @@
 #include "render_bwd_tiled.cuh"
 #include "render_shift.cuh"
 #include "render_tiled.cuh"
+#include "render_fwd.cuh"
 #include "warp_ops.cuh"
 #include "pil_composite.cuh"
 
@@ -69,24 +70,35 @@ template <typename T, bool kRagged>
 int launch_forward_tiled(const void* x, const SrcLayers& src, const float* theta, void* out, void* sav, const mgr::Geometry& g,
                          cudaStream_t s) {
   using Vec = typename Texel<T>::Vec;
-  const size_t smem = tiled_smem_bytes(g.L, sizeof(Vec));
+  const size_t smem_a = tiled_smem_bytes(g.L, sizeof(Vec)), smem_b = shift_fwd_smem_bytes(g.L, sizeof(Vec));
+  const size_t smem = smem_a > smem_b ? smem_a : smem_b;      // one launch serves both code paths (render_fwd.cuh)
   static bool configured = false;   // per instantiation; attribute is sticky per function
   if (!configured) {
-    MGR_CUDA(cudaFuncSetAttribute(render_fwd_tiled<T, false, kRagged>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    MGR_CUDA(cudaFuncSetAttribute(render_fwd_tiled<T, true, kRagged>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    MGR_CUDA(cudaFuncSetAttribute(render_fwd<T, false, kRagged>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    MGR_CUDA(cudaFuncSetAttribute(render_fwd<T, true, kRagged>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     configured = true;
   }
   dim3 grid((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B);
   using SA = typename SavedAlpha<T>::type;
-  const int shift = debug_path() != 2;        // all-translation samples go to the stencil kernel
-  if (sav) render_fwd_tiled<T, true, kRagged><<<grid, kTiledThreads, smem, s>>>((const T*)x, src, theta, (T*)out, (SA*)sav, g, shift);
-  else render_fwd_tiled<T, false, kRagged><<<grid, kTiledThreads, smem, s>>>((const T*)x, src, theta, (T*)out, nullptr, g, shift);
-  if (shift) {
-    MGR_CUDA(cudaGetLastError());
-    count_launch();
-    const size_t smem2 = shift_fwd_smem_bytes(g.L, sizeof(Vec));
-    if (sav) render_fwd_shift<T, true><<<grid, kTiledThreads, smem2, s>>>(src, theta, (T*)out, (SA*)sav, g);
-    else render_fwd_shift<T, false><<<grid, kTiledThreads, smem2, s>>>(src, theta, (T*)out, nullptr, g);
+  const int stencil = debug_path() != 2;        // all-translation samples take the stencil path
+  if constexpr (sizeof(T) == 4) {               // fp32: one launch per path (see render_fwd.cuh)
+    static bool configured32 = false;
+    if (!configured32) {
+      MGR_CUDA(cudaFuncSetAttribute(render_fwd_general_only<T, false, kRagged>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      MGR_CUDA(cudaFuncSetAttribute(render_fwd_general_only<T, true, kRagged>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      configured32 = true;
+    }
+    if (sav) render_fwd_general_only<T, true, kRagged><<<grid, kTiledThreads, smem_a, s>>>((const T*)x, src, theta, (T*)out, (SA*)sav, g, stencil);
+    else render_fwd_general_only<T, false, kRagged><<<grid, kTiledThreads, smem_a, s>>>((const T*)x, src, theta, (T*)out, nullptr, g, stencil);
+    if (stencil) {
+      MGR_CUDA(cudaGetLastError());
+      count_launch();
+      if (sav) render_fwd_stencil_only<T, true><<<grid, kTiledThreads, smem_b, s>>>(src, theta, (T*)out, (SA*)sav, g);
+      else render_fwd_stencil_only<T, false><<<grid, kTiledThreads, smem_b, s>>>(src, theta, (T*)out, nullptr, g);
+    }
+  } else {
+    if (sav) render_fwd<T, true, kRagged><<<grid, kTiledThreads, smem, s>>>((const T*)x, src, theta, (T*)out, (SA*)sav, g, stencil);
+    else render_fwd<T, false, kRagged><<<grid, kTiledThreads, smem, s>>>((const T*)x, src, theta, (T*)out, nullptr, g, stencil);
   }
   MGR_CUDA(cudaGetLastError());
   count_launch();

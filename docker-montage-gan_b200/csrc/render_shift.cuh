@@ -65,9 +65,8 @@ constexpr int kShiftCap = (kTW + 2 * kStageVec) * (kTH + 1);        // staged te
 // forward
 // ---------------------------------------------------------------------------------------------
 template <typename T, bool kSave>
-__global__ void __launch_bounds__(kTiledThreads, MGR_SHF_BLOCKS)
-render_fwd_shift(const __grid_constant__ SrcLayers src, const float* __restrict__ theta, T* __restrict__ out,
-                 typename SavedAlpha<T>::type* __restrict__ sav, Geometry g) {
+__device__ __forceinline__ void fwd_shift_body(const SrcLayers& src, const float* __restrict__ theta, T* __restrict__ out,
+                                               typename SavedAlpha<T>::type* __restrict__ sav, const Geometry& g) {
   using Vec = typename Texel<T>::Vec;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Vec* buf = reinterpret_cast<Vec*>(smem_raw);                                           // [kShiftCap]
@@ -75,7 +74,6 @@ render_fwd_shift(const __grid_constant__ SrcLayers src, const float* __restrict_
   const int tid = threadIdx.x;
   const int b = blockIdx.z;
   const float* thb = theta + (long long)b * g.L * 6;
-  if (!cta_all_shift(thb, g.L, tid, kTiledThreads)) return;
   const int j0 = blockIdx.x * kTW, i0 = blockIdx.y * kTH;
   const int tx = tid & 31, ty = tid >> 5;                    // pixels (tx, 4 ty + k), k = 0..3
   for (int l = tid; l < g.L; l += kTiledThreads) splan[l] = make_shift_plan(thb + 6 * l, g.H, g.W);

@@ -45,17 +45,15 @@ __device__ __noinline__ float4 sample_pixel_direct(const T* __restrict__ img, co
 #define MGR_FWD_BLOCKS 3
 #endif
 template <typename T, bool kSave, bool kRagged>
-__global__ void __launch_bounds__(kTiledThreads, MGR_FWD_BLOCKS)
-render_fwd_tiled(const T* __restrict__ x, const __grid_constant__ SrcLayers src, const float* __restrict__ theta, T* __restrict__ out,
-                 typename SavedAlpha<T>::type* __restrict__ sav, Geometry g, int skip_shift) {
+__device__ __forceinline__ void fwd_tiled_body(const T* __restrict__ x, const SrcLayers& src, const float* __restrict__ theta,
+                                               T* __restrict__ out, typename SavedAlpha<T>::type* __restrict__ sav,
+                                               const Geometry& g) {
   using Vec = typename Texel<T>::Vec;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Vec* buf = reinterpret_cast<Vec*>(smem_raw);                                            // [kCapTexels]
   LayerPlan* plan = reinterpret_cast<LayerPlan*>(smem_raw + sizeof(Vec) * kCapTexels);    // [L]
   const int tid = threadIdx.x;
   const int b = blockIdx.z;
-  // all-translation samples belong to render_fwd_shift (render_shift.cuh)
-  if (skip_shift && cta_all_shift(theta + (long long)b * g.L * 6, g.L, tid, kTiledThreads)) return;
   const int j0 = blockIdx.x * kTW, i0 = blockIdx.y * kTH;
   const int tx = tid & 31, ty = tid >> 5;
   for (int l = tid; l < g.L; l += kTiledThreads)
