@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libmontage_render.so")
 MGR_F32, MGR_BF16, MGR_F16 = 0, 1, 2
 MGR_RANGE_M11, MGR_RANGE_01 = 0, 1
 MGR_NEED_GRAD_X, MGR_NEED_GRAD_THETA = 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _c = ctypes
 _vp, _i, _sz = _c.c_void_p, _c.c_int, _c.c_size_t

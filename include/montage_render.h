@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define MGR_ABI_VERSION 2
+#define MGR_ABI_VERSION 3
 
 enum { MGR_F32 = 0, MGR_BF16 = 1, MGR_F16 = 2 };
 enum { MGR_RANGE_M11 = 0, MGR_RANGE_01 = 1 };

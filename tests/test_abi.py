@@ -78,7 +78,7 @@ def test_backward_validation_and_workspace():
     lib = _lib.load()
     assert lib.mgr_render_backward_workspace_bytes(2, 3, 8, 8, _lib.MGR_F32, 0, 3) == 0      # composite only
     assert lib.mgr_render_backward_workspace_bytes(2, 3, 8, 8, _lib.MGR_BF16, 0, 1) == 0
-    assert lib.mgr_render_backward_workspace_bytes(2, 3, 8, 8, _lib.MGR_F32, 1, 3) == 2 * 3 * 64 * 8 + 2 * 64 * 16 + 2 * 3 * (128 + 4) + 16
+    assert lib.mgr_render_backward_workspace_bytes(2, 3, 8, 8, _lib.MGR_F32, 1, 3) == 2 * 3 * 64 * 8 + 2 * 64 * 16 + 2 * 3 * (128 + 4 + 4) + 32 + 2 * 4   # records, G_P, plans + order + work list, counters, sample flags
     assert lib.mgr_saved_alpha_bytes(2, 3, 8, 8, _lib.MGR_F32) == 2 * 3 * 64 * 4
     assert lib.mgr_saved_alpha_bytes(2, 3, 8, 8, _lib.MGR_BF16) == 2 * 3 * 64 * 2
     need = lib.mgr_render_backward_workspace_bytes(2, 3, 8, 8, _lib.MGR_BF16, 1, 3)
