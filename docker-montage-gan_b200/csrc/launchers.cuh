@@ -193,8 +193,15 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
   MGR_CUDA(cudaGetLastError());
   count_launch();
   if (nx) {
-    dim3 grid2((g.W + kP2W - 1) / kP2W, (g.H + kP2H - 1) / kP2H, g.B * g.L);
-    render_bwd_pass2<T, kRagged><<<grid2, 256, 0, s>>>(inv, work, wcnt, rec, gp, (T*)gx, dst, g);
+    // square 32 x 32 texel blocks for big launches, 64 x 16 when a heavy layer's blocks would be the tail (see P2Shape)
+    const long long blocks = (long long)((g.W + 31) / 32) * ((g.H + 31) / 32) * g.B * g.L;
+    if (blocks >= 16384) {
+      dim3 grid2((g.W + 31) / 32, (g.H + 31) / 32, g.B * g.L);
+      render_bwd_pass2<T, kRagged, 16><<<grid2, 256, 0, s>>>(inv, work, wcnt, rec, gp, (T*)gx, dst, g);
+    } else {
+      dim3 grid2((g.W + 63) / 64, (g.H + 15) / 16, g.B * g.L);
+      render_bwd_pass2<T, kRagged, 32><<<grid2, 256, 0, s>>>(inv, work, wcnt, rec, gp, (T*)gx, dst, g);
+    }
     MGR_CUDA(cudaGetLastError());
     count_launch();
   }

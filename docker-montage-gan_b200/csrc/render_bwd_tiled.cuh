@@ -334,7 +334,11 @@ sample_flags_kernel(InverseLayer* __restrict__ plans, int B, int L, const int* _
 // Block of 256 threads = 32 x 8 threads, each owning a 2 x 2 block of texels -> 64 x 16 texels per CTA.
 // A 2 x 2 block shares its candidate pixels (the union of four windows is barely larger than one), the
 // record loads and the per-candidate coordinate arithmetic; the accumulators are packed fp32x2 pairs.
-constexpr int kP2W = 64, kP2H = 16;
+// Block shape: kTX threads along x (each thread 2 x 2 texels).  kTX = 16 -> 32 x 32 texels: the candidate pixels of
+// neighbouring threads overlap more (-2.4 % backward at B*L >= 448 layers); kTX = 32 -> 64 x 16 texels: shorter blocks,
+// which matters when a near-singular layer's blocks are the tail of a small launch (+15 us at B = 8..16 otherwise).
+// The host picks by the number of blocks in the launch (launchers.cuh).
+template <int kTX> struct P2Shape { static constexpr int kTY = 256 / kTX, kW = 2 * kTX, kH = 2 * kTY; };
 
 template <typename T> struct Pack2;      // two horizontally adjacent texels of one channel -> one (aligned) store
 template <> struct Pack2<float> {
@@ -359,14 +363,15 @@ __device__ __forceinline__ float hat(float u) { return fmaxf(1.f - fabsf(u), 0.f
 #define MGR_P2_BLOCKS 4
 #endif
 // one 64 x 16 texel block of layer n = b * L + l
-template <typename T, bool kRagged>
+template <typename T, bool kRagged, int kP2TX>
 __device__ __forceinline__ void pass2_block(const InverseLayer* __restrict__ plans, int n, int x0b, int y0b,
                                             const float2* __restrict__ rec, const float4* __restrict__ gp, T* __restrict__ gx,
                                             const DstLayers& dst, const Geometry& g) {
+  constexpr int kP2W = P2Shape<kP2TX>::kW, kP2H = P2Shape<kP2TX>::kH;
   __shared__ float s_jcf, s_icf;
   __shared__ int s_JC, s_IC, s_ok;
   const int b = n / g.L;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int tx = threadIdx.x % kP2TX, ty = threadIdx.x / kP2TX;
   const InverseLayer& L_ = plans[n];
   const int hw = g.H * g.W;
   const int x = x0b + 2 * tx, y = y0b + 2 * ty;                // top-left texel of this thread's 2 x 2 block (canvas coordinates)
@@ -567,13 +572,14 @@ __device__ __forceinline__ void pass2_block(const InverseLayer* __restrict__ pla
 // One CTA per (layer of the work list, 64 x 16 texel block).  The grid's z extent is B * L (the host cannot know how
 // many layers the work list holds); CTAs beyond wcnt[0] leave after that one load -- for a batch of translations that
 // is all of them.  (Walking the items inside persistent or grid-stride CTAs was measured 3-8 % slower on general batches.)
-template <typename T, bool kRagged>
+template <typename T, bool kRagged, int kTX>
 __global__ void __launch_bounds__(256, MGR_P2_BLOCKS)
 render_bwd_pass2(const InverseLayer* __restrict__ plans, const int* __restrict__ work, const int* __restrict__ wcnt,
                  const float2* __restrict__ rec, const float4* __restrict__ gp, T* __restrict__ gx,
                  const __grid_constant__ DstLayers dst, Geometry g) {
   if ((int)blockIdx.z >= wcnt[0]) return;
-  pass2_block<T, kRagged>(plans, work[blockIdx.z], blockIdx.x * kP2W, blockIdx.y * kP2H, rec, gp, gx, dst, g);
+  pass2_block<T, kRagged, kTX>(plans, work[blockIdx.z], blockIdx.x * P2Shape<kTX>::kW, blockIdx.y * P2Shape<kTX>::kH, rec, gp, gx,
+                               dst, g);
 }
 
 }  // namespace mgr
