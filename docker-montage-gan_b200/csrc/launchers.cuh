@@ -7,6 +7,7 @@
 #include "render_tiled.cuh"
 #include "render_fwd.cuh"
 #include "warp_ops.cuh"
+#include "warp_tiled.cuh"
 #include "pil_composite.cuh"
 
 namespace mgr {
@@ -257,6 +258,18 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
 // ---- materialised warp and staging helpers (warp_ops.cuh) -----------------------------------------
 template <typename T>
 int launch_warp_forward(const void* x, const float* theta, void* out, const Geometry& g, cudaStream_t s) {
+  if (tiled_ok<T>(x, g)) {                                     // staged footprints, one layer per CTA (warp_tiled.cuh)
+    static bool configured = false;
+    if (!configured) {
+      MGR_CUDA(cudaFuncSetAttribute(warp_fwd_tiled<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      configured = true;
+    }
+    dim3 gridt((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B * g.L);
+    warp_fwd_tiled<T><<<gridt, kTiledThreads, sizeof(typename Texel<T>::Vec) * kCapTexels, s>>>((const T*)x, theta, (T*)out, g);
+    MGR_CUDA(cudaGetLastError());
+    count_launch();
+    return MGR_OK;
+  }
   dim3 grid((g.W + kTileW - 1) / kTileW, (g.H + kTileH - 1) / kTileH, g.B * g.L);
   warp_fwd_kernel<T><<<grid, kDirectThreads, 0, s>>>((const T*)x, theta, (T*)out, g);
   MGR_CUDA(cudaGetLastError());
@@ -269,6 +282,42 @@ int launch_warp_backward(const void* x, const float* theta, const void* gout, vo
                          const Geometry& g, int flags, cudaStream_t s) {
   const long long n = (long long)g.B * g.L * 4 * g.H * g.W;
   const bool nx = flags & MGR_NEED_GRAD_X, nt = flags & MGR_NEED_GRAD_THETA;
+  if (tiled_ok<T>(x, g)) {
+    // atomics-free: gather-form adjoint for grad_x, staged footprints + per-CTA reduction for grad_theta (warp_tiled.cuh)
+    using Vec = typename Texel<T>::Vec;
+    InverseLayer* inv = reinterpret_cast<InverseLayer*>(ws);
+    int* order = reinterpret_cast<int*>(inv + (size_t)g.B * g.L);
+    int* work = order + (size_t)g.B * g.L + 2;
+    int* wcnt = work + (size_t)g.B * g.L;
+    int* sflag = wcnt + 2;
+    if (nx) {
+      MGR_CUDA(cudaMemsetAsync(order + g.B * g.L, 0, 2 * sizeof(int), s));
+      inverse_plans_kernel<<<(g.B * g.L + 127) / 128, 128, 0, s>>>(theta, inv, g.B * g.L, g.H, g.W, order, order + g.B * g.L);
+      sample_flags_kernel<<<1, 256, 0, s>>>(inv, g.B, g.L, order, work, wcnt, sflag, 0);      // every layer stays in the work list
+      MGR_CUDA(cudaGetLastError());
+      count_launch(2);
+      const long long blocks = (long long)((g.W + 31) / 32) * ((g.H + 31) / 32) * g.B * g.L;
+      if (blocks >= 16384) {
+        dim3 grid2((g.W + 31) / 32, (g.H + 31) / 32, g.B * g.L);
+        warp_bwd_gather<T, 16><<<grid2, 256, 0, s>>>(inv, work, wcnt, (const T*)gout, (T*)gx, g);
+      } else {
+        dim3 grid2((g.W + 63) / 64, (g.H + 15) / 16, g.B * g.L);
+        warp_bwd_gather<T, 32><<<grid2, 256, 0, s>>>(inv, work, wcnt, (const T*)gout, (T*)gx, g);
+      }
+      MGR_CUDA(cudaGetLastError());
+      count_launch();
+    }
+    if (nt) {
+      MGR_CUDA(cudaMemsetAsync(gtheta, 0, sizeof(float) * 6 * g.B * g.L, s));
+      const size_t smem = sizeof(Vec) * kCapTexels + sizeof(float) * kPx * kTiledThreads;
+      MGR_CUDA(cudaFuncSetAttribute(warp_bwd_theta_tiled<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      dim3 gridt((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B * g.L);
+      warp_bwd_theta_tiled<T><<<gridt, kTiledThreads, smem, s>>>((const T*)x, theta, (const T*)gout, gtheta, g);
+      MGR_CUDA(cudaGetLastError());
+      count_launch();
+    }
+    return MGR_OK;
+  }
   float* gx32 = nullptr;
   if (nx) {
     gx32 = (sizeof(T) == 4) ? (float*)gx : (float*)ws;

@@ -157,8 +157,14 @@ int mgr_warp_forward(const void* x, const int64_t* x_strides, const float* theta
 
 size_t mgr_warp_backward_workspace_bytes(int B, int L, int H, int W, int dtype, int flags) {
   if (B <= 0 || L <= 0 || H <= 0 || W <= 0) return 0;
-  if ((flags & MGR_NEED_GRAD_X) && dtype != MGR_F32) return sizeof(float) * (size_t)B * L * 4 * H * W;
-  return 0;
+  // gather path: per layer an inverse placement, a launch-order entry and a work-list entry; counters; a flag per sample
+  size_t need = (size_t)B * L * (128 + 4 + 4) + 32 + (size_t)B * 4;
+  // scatter path (odd widths / strides): an fp32 accumulator for 16-bit tensors
+  if ((flags & MGR_NEED_GRAD_X) && dtype != MGR_F32) {
+    const size_t scatter = sizeof(float) * (size_t)B * L * 4 * H * W;
+    if (scatter > need) need = scatter;
+  }
+  return need;
 }
 
 int mgr_warp_backward(const void* x, const int64_t* x_strides, const float* theta, const void* grad_out,

@@ -362,12 +362,45 @@ __device__ __forceinline__ float hat(float u) { return fmaxf(1.f - fabsf(u), 0.f
 #ifndef MGR_P2_BLOCKS
 #define MGR_P2_BLOCKS 4
 #endif
-// one 64 x 16 texel block of layer n = b * L + l
-template <typename T, bool kRagged, int kP2TX>
-__device__ __forceinline__ void pass2_block(const InverseLayer* __restrict__ plans, int n, int x0b, int y0b,
-                                            const float2* __restrict__ rec, const float4* __restrict__ gp, T* __restrict__ gx,
-                                            const DstLayers& dst, const Geometry& g) {
+// Where the gather reads the gradient w.r.t. one warped sample (g_rgb, g_a) of an output pixel of the layer:
+//   CompositeRecords: the fused renderer's pass-1 output -- (T_l a_l, d a_l) per layer-pixel times (G_P, .) per pixel;
+//   PlanarGrads<T>:   the upstream gradient of MATERIALISED warped layers, four planes of T (mgr_warp_backward).
+// A cursor points at a pixel; at(off) / advance(off) move it by pixels, load(mm) reads the pixel mm further on.
+struct CompositeRecords {
+  const float2* r;
+  const float4* g;
+  __device__ __forceinline__ CompositeRecords layer(int n, int b, int hw) const {    // from the tensors' first element
+    return CompositeRecords{r + (long long)n * hw, g + (long long)b * hw};
+  }
+  __device__ __forceinline__ CompositeRecords at(int off) const { return CompositeRecords{r + off, g + off}; }
+  __device__ __forceinline__ void advance(int off) { r += off; g += off; }
+  __device__ __forceinline__ void load(int mm, f32x2& grg, f32x2& gba) const {
+    const float2 rr = __ldg(r + mm);
+    const float4 G = __ldg(g + mm);
+    grg = pk(G.x * rr.x, G.y * rr.x);
+    gba = pk(G.z * rr.x, rr.y);
+  }
+};
+template <typename T>
+struct PlanarGrads {
+  const T* p;
+  int hw;
+  __device__ __forceinline__ PlanarGrads layer(int n, int, int hw_) const { return PlanarGrads{p + (long long)n * 4 * hw_, hw_}; }
+  __device__ __forceinline__ PlanarGrads at(int off) const { return PlanarGrads{p + off, hw}; }
+  __device__ __forceinline__ void advance(int off) { p += off; }
+  __device__ __forceinline__ void load(int mm, f32x2& grg, f32x2& gba) const {
+    grg = pk(ld(p + mm), ld(p + hw + mm));
+    gba = pk(ld(p + 2 * hw + mm), ld(p + 3 * hw + mm));
+  }
+};
+
+// one block of 2 kTX x 2 (256 / kTX) texels of layer n = b * L + l; `src` points at the first element of the
+// gradient-record tensors; zs = d(sampled value) / d(texel) apart from the bilinear weight
+template <typename T, bool kRagged, int kP2TX, typename Src>
+__device__ __forceinline__ void pass2_block(const InverseLayer* __restrict__ plans, int n, int x0b, int y0b, const Src src,
+                                            float zs, T* __restrict__ gx, const DstLayers* dst, const Geometry& g) {
   constexpr int kP2W = P2Shape<kP2TX>::kW, kP2H = P2Shape<kP2TX>::kH;
+  constexpr bool kComposite = std::is_same<Src, CompositeRecords>::value;
   __shared__ float s_jcf, s_icf;
   __shared__ int s_JC, s_IC, s_ok;
   const int b = n / g.L;
@@ -375,10 +408,9 @@ __device__ __forceinline__ void pass2_block(const InverseLayer* __restrict__ pla
   const InverseLayer& L_ = plans[n];
   const int hw = g.H * g.W;
   const int x = x0b + 2 * tx, y = y0b + 2 * ty;                // top-left texel of this thread's 2 x 2 block (canvas coordinates)
-  const float zs = g.m11 ? 0.5f : 1.f;          // d z / d x_texel = zs * weight
   // the layer's own pixels: a rectangle of the canvas (the whole canvas in the [B,L,4,H,W] layout); left, w even
   DstLayer dl;
-  if (kRagged) dl = dst.s[n - b * g.L];
+  if (kRagged) dl = dst->s[n - b * g.L];
   else dl = DstLayer{gx + (long long)(n - b * g.L) * 4 * hw, (long long)g.L * 4 * hw, hw, g.W, g.H, g.W, 0, 0};
   const int xl = x - dl.left, yl = y - dl.top;
   const bool mine = (unsigned)xl < (unsigned)dl.w && yl >= -1 && yl < dl.h;      // at least one of the block's rows is inside
@@ -394,8 +426,6 @@ __device__ __forceinline__ void pass2_block(const InverseLayer* __restrict__ pla
     // weights (dx ? fx : 1 - fx)(dy ? fy : 1 - fy): a fixed 2 x 2 stencil; the 2 x 2 block reads 3 x 3 records
     if (!mine) return;
     const float wx[2] = {1.f - L_.fx, L_.fx}, wy[2] = {1.f - L_.fy, L_.fy};
-    const float2* recn = rec + (long long)n * hw;
-    const float4* gpb = gp + (long long)b * hw;
 #pragma unroll
     for (int di = -1; di <= 1; ++di) {
       const int i = y - L_.Y + di;
@@ -404,9 +434,8 @@ __device__ __forceinline__ void pass2_block(const InverseLayer* __restrict__ pla
       for (int dj = -1; dj <= 1; ++dj) {
         const int j = x - L_.X + dj;
         if ((unsigned)j >= (unsigned)g.W) continue;
-        const float2 r = __ldg(recn + i * g.W + j);
-        const float4 G = __ldg(gpb + i * g.W + j);
-        const f32x2 grg = pk(G.x * r.x, G.y * r.x), gba = pk(G.z * r.x, r.y);
+        f32x2 grg, gba;
+        src.layer(n, b, hw).load(i * g.W + j, grg, gba);
 #pragma unroll
         for (int ky = 0; ky < 2; ++ky) {
           const int ty_ = ky - di;              // tap row index of texel row ky for this pixel: (y + ky) - (i + Y)
@@ -450,8 +479,7 @@ __device__ __forceinline__ void pass2_block(const InverseLayer* __restrict__ pla
     const bool has = s_ok && mine && mlo <= mhi && nlo <= nhi;
     if (!has) { mlo = 0.f; mhi = -1.f; nlo = 0.f; nhi = -1.f; }
     float x0l = dxl - 0.5f, y0l = dyl - 0.5f;                  // texel (0,0) of the block relative to the CTA centre
-    const float2* rec0 = rec + (long long)n * hw + (IC * g.W + JC);
-    const float4* gp0 = gp + (long long)b * hw + (IC * g.W + JC);
+    const Src src0 = src.layer(n, b, hw).at(IC * g.W + JC);
 
     // one candidate row nn of the window (mlo_..mhi_) of the block at (x0l_, y0l_), accumulated into acc_
     auto row = [&](int nn, float mlo_, float mhi_, float x0l_, float y0l_, f32x2 (&acc_)[2][2][2]) {
@@ -478,14 +506,12 @@ __device__ __forceinline__ void pass2_block(const InverseLayer* __restrict__ pla
       const float dja = lo - jcf;
       float u = fmaf(a00, dja, ub);                            // ix(candidate) - x of texel column 0
       float v = fmaf(a10, dja, vb);                            // iy(candidate) - y of texel row 0
-      const float2* recn = rec0 + nn * g.W;
-      const float4* gpb = gp0 + nn * g.W;
+      const Src cur = src0.at(nn * g.W);
 #pragma unroll 1
       for (int mm = ma; mm <= mb; ++mm, u += a00, v += a10) {
         const float wx0 = hat(u), wx1 = hat(u - 1.f), wy0 = hat(v), wy1 = hat(v - 1.f);
-        const float2 r = __ldg(recn + mm);
-        const float4 G = __ldg(gpb + mm);
-        const f32x2 grg = pk(G.x * r.x, G.y * r.x), gba = pk(G.z * r.x, r.y);
+        f32x2 grg, gba;
+        cur.load(mm, grg, gba);
         const f32x2 w00 = bc(wy0 * wx0), w01 = bc(wy0 * wx1), w10 = bc(wy1 * wx0), w11 = bc(wy1 * wx1);
         acc_[0][0][0] = fma2(w00, grg, acc_[0][0][0]); acc_[0][0][1] = fma2(w00, gba, acc_[0][0][1]);
         acc_[0][1][0] = fma2(w01, grg, acc_[0][1][0]); acc_[0][1][1] = fma2(w01, gba, acc_[0][1][1]);
@@ -500,23 +526,33 @@ __device__ __forceinline__ void pass2_block(const InverseLayer* __restrict__ pla
         const int m0 = (int)mlo, m1 = (int)mhi, n0 = (int)nlo, n1 = (int)nhi;
         const float dj0 = mlo - jcf;
         float di = nlo - icf;
-        const float2* recn = rec0 + n0 * g.W;
-        const float4* gpb = gp0 + n0 * g.W;
-        for (int nn = n0; nn <= n1; ++nn, di += 1.f, recn += g.W, gpb += g.W) {
+        // (the two row pointers are spelled out: a cursor object costs the fused renderer's hot loop six instructions
+        //  after register allocation)
+        Src cur = src0.at(n0 * g.W);
+        const float2* recn = nullptr;
+        const float4* gpb = nullptr;
+        if constexpr (kComposite) { recn = src0.r + n0 * g.W; gpb = src0.g + n0 * g.W; }
+        for (int nn = n0; nn <= n1; ++nn, di += 1.f) {
           float u = fmaf(a00, dj0, fmaf(a01, di, -x0l));
           float v = fmaf(a10, dj0, fmaf(a11, di, -y0l));
 #pragma unroll 1
           for (int mm = m0; mm <= m1; ++mm, u += a00, v += a10) {
             const float wx0 = hat(u), wx1 = hat(u - 1.f), wy0 = hat(v), wy1 = hat(v - 1.f);
-            const float2 r = __ldg(recn + mm);
-            const float4 G = __ldg(gpb + mm);
-            const f32x2 grg = pk(G.x * r.x, G.y * r.x), gba = pk(G.z * r.x, r.y);
+            f32x2 grg, gba;
+            if constexpr (kComposite) {
+              const float2 r = __ldg(recn + mm);
+              const float4 G = __ldg(gpb + mm);
+              grg = pk(G.x * r.x, G.y * r.x); gba = pk(G.z * r.x, r.y);
+            } else {
+              cur.load(mm, grg, gba);
+            }
             const f32x2 w00 = bc(wy0 * wx0), w01 = bc(wy0 * wx1), w10 = bc(wy1 * wx0), w11 = bc(wy1 * wx1);
             acc[0][0][0] = fma2(w00, grg, acc[0][0][0]); acc[0][0][1] = fma2(w00, gba, acc[0][0][1]);
             acc[0][1][0] = fma2(w01, grg, acc[0][1][0]); acc[0][1][1] = fma2(w01, gba, acc[0][1][1]);
             acc[1][0][0] = fma2(w10, grg, acc[1][0][0]); acc[1][0][1] = fma2(w10, gba, acc[1][0][1]);
             acc[1][1][0] = fma2(w11, grg, acc[1][1][0]); acc[1][1][1] = fma2(w11, gba, acc[1][1][1]);
           }
+          if constexpr (kComposite) { recn += g.W; gpb += g.W; } else { cur.advance(g.W); }
         }
       }
     } else {
@@ -578,8 +614,8 @@ render_bwd_pass2(const InverseLayer* __restrict__ plans, const int* __restrict__
                  const float2* __restrict__ rec, const float4* __restrict__ gp, T* __restrict__ gx,
                  const __grid_constant__ DstLayers dst, Geometry g) {
   if ((int)blockIdx.z >= wcnt[0]) return;
-  pass2_block<T, kRagged, kTX>(plans, work[blockIdx.z], blockIdx.x * P2Shape<kTX>::kW, blockIdx.y * P2Shape<kTX>::kH, rec, gp, gx,
-                               dst, g);
+  pass2_block<T, kRagged, kTX>(plans, work[blockIdx.z], blockIdx.x * P2Shape<kTX>::kW, blockIdx.y * P2Shape<kTX>::kH,
+                               CompositeRecords{rec, gp}, g.m11 ? 0.5f : 1.f, gx, &dst, g);
 }
 
 }  // namespace mgr

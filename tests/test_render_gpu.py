@@ -270,8 +270,9 @@ def test_tiled_kernels_match_direct_kernels(dtype, tf):
 # --------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("in_range", ["m11", "01"])
 @pytest.mark.parametrize("tf", ["I", "T"])
-def test_warp_matches_oracle(in_range, tf):
-    B, L, H, W = 2, 5, 40, 48
+@pytest.mark.parametrize("hw", [(40, 48), (72, 64), (33, 46)])      # tiled kernels (W % 4 == 0) and the direct fallback
+def test_warp_matches_oracle(in_range, tf, hw):
+    B, L, (H, W) = 2, 5, hw
     x = synth.make_layers(B, L, H, W, "W", seed=8)
     if in_range == "01":
         x = (x + 1) / 2
