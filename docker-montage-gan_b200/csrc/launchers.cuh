@@ -9,6 +9,7 @@
 #include "warp_ops.cuh"
 #include "warp_tiled.cuh"
 #include "pil_composite.cuh"
+#include "composite_only.cuh"
 
 namespace mgr {
 
@@ -22,6 +23,13 @@ bool tiled_ok(const void* x, const Geometry& g) {
   const long long layer_bytes = (3 * g.sc + (long long)g.H * g.sh) * (long long)sizeof(T);   // 32-bit offsets inside a layer
   return (g.L <= kMaxTiledLayers) && (g.W % v == 0) && (g.sh % v == 0) && (g.sc % v == 0) && (g.sl % v == 0) && (g.sb % v == 0) &&
          (reinterpret_cast<uintptr_t>(x) % (kStageVec * sizeof(T)) == 0) && g.sc >= 0 && (long long)g.H * g.W < (1LL << 29) && layer_bytes < (1LL << 31);
+}
+
+// four adjacent pixels per thread (composite_only.cuh): rows, planes and base 4-element aligned
+template <typename T>
+bool vec4_ok(const void* x, const Geometry& g) {
+  return g.W % 4 == 0 && g.sh % 4 == 0 && g.sc % 4 == 0 && g.sl % 4 == 0 && g.sb % 4 == 0 &&
+         reinterpret_cast<uintptr_t>(x) % (4 * sizeof(T)) == 0;
 }
 
 // the canvas layout x[B,L,4,H,W] / grad_x[B,L,4,H,W] as per-layer descriptors (every layer covers the whole canvas)
@@ -109,6 +117,13 @@ int launch_forward_tiled(const void* x, const SrcLayers& src, const float* theta
 template <typename T>
 int launch_forward(const void* x, const float* theta, void* out, void* sav, const mgr::Geometry& g, cudaStream_t s) {
   if (theta && g.L >= 2 && tiled_ok<T>(x, g)) return launch_forward_tiled<T, false>(x, canvas_src<T>(x, g), theta, out, sav, g, s);
+  if (!theta && g.L >= 2 && vec4_ok<T>(x, g) && reinterpret_cast<uintptr_t>(out) % (4 * sizeof(T)) == 0 && debug_path() != 1) {
+    const long long blocks = ((long long)g.B * g.H * (g.W / 4) + 255) / 256;     // streaming composite, 4 px per thread
+    composite_fwd_vec<T><<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, s>>>((const T*)x, (T*)out, g);
+    MGR_CUDA(cudaGetLastError());
+    count_launch();
+    return MGR_OK;
+  }
   dim3 grid((g.W + mgr::kTileW - 1) / mgr::kTileW, (g.H + mgr::kTileH - 1) / mgr::kTileH, g.B);
   const size_t smem = sizeof(mgr::TileAffine) * g.L;
   if (theta)

@@ -29,6 +29,55 @@ struct Geometry {
   int m11;                   // 1: [-1,1] range mode, 0: [0,1]
 };
 
+// kVec adjacent elements -> fp32 (kVec = 4: one 16- or 8-byte load; the caller guarantees the alignment)
+template <typename T, int kVec> struct VecIO;
+template <typename T> struct VecIO<T, 1> {
+  static __device__ __forceinline__ void ld(const T* p, float (&v)[1]) { v[0] = mgr::ld(p); }
+};
+template <> struct VecIO<float, 4> {
+  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+};
+template <> struct VecIO<__nv_bfloat16, 4> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[4]) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
+    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
+  }
+};
+template <> struct VecIO<__half, 4> {
+  static __device__ __forceinline__ void ld(const __half* p, float (&v)[4]) {
+    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+};
+template <typename T, int kVec> __device__ __forceinline__ void ld_vec(const T* p, float (&v)[kVec]) { VecIO<T, kVec>::ld(p, v); }
+template <int kVec> __device__ __forceinline__ void st_vec_f32(float* p, const float (&v)[kVec]) {
+  if constexpr (kVec == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  else p[0] = v[0];
+}
+
+template <typename T> __device__ __forceinline__ void st_vec4(T* p, const float (&v)[4]);      // four adjacent elements, aligned
+template <> __device__ __forceinline__ void st_vec4<float>(float* p, const float (&v)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+template <> __device__ __forceinline__ void st_vec4<__nv_bfloat16>(__nv_bfloat16* p, const float (&v)[4]) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 t;
+  t.x = *reinterpret_cast<const uint32_t*>(&a); t.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+template <> __device__ __forceinline__ void st_vec4<__half>(__half* p, const float (&v)[4]) {
+  const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+  uint2 t;
+  t.x = *reinterpret_cast<const uint32_t*>(&a); t.y = *reinterpret_cast<const uint32_t*>(&b);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+
 // Where one layer's pixels live.  The canvas layout x[B,L,4,H,W] is the special case {x + l*sl, sb, sc, sh, H, W, 0, 0};
 // the ragged layout (the local generators' outputs at native size, custom_utils/image_utils.py:216-243
 // without the padded copy) gives every layer its own [B,4,h,w] tensor centred at (left, top) of the H x W canvas.

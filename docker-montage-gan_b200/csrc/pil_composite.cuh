@@ -14,38 +14,6 @@
 
 namespace mgr {
 
-// kVec adjacent elements -> fp32 (kVec = 4: one 16- or 8-byte load; the caller guarantees the alignment)
-template <typename T, int kVec> struct VecIO;
-template <typename T> struct VecIO<T, 1> {
-  static __device__ __forceinline__ void ld(const T* p, float (&v)[1]) { v[0] = mgr::ld(p); }
-};
-template <> struct VecIO<float, 4> {
-  static __device__ __forceinline__ void ld(const float* p, float (&v)[4]) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(p));
-    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-  }
-};
-template <> struct VecIO<__nv_bfloat16, 4> {
-  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[4]) {
-    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
-    v[0] = __uint_as_float(t.x << 16); v[1] = __uint_as_float(t.x & 0xffff0000u);
-    v[2] = __uint_as_float(t.y << 16); v[3] = __uint_as_float(t.y & 0xffff0000u);
-  }
-};
-template <> struct VecIO<__half, 4> {
-  static __device__ __forceinline__ void ld(const __half* p, float (&v)[4]) {
-    const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&t.y));
-    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
-  }
-};
-template <typename T, int kVec> __device__ __forceinline__ void ld_vec(const T* p, float (&v)[kVec]) { VecIO<T, kVec>::ld(p, v); }
-template <int kVec> __device__ __forceinline__ void st_vec_f32(float* p, const float (&v)[kVec]) {
-  if constexpr (kVec == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
-  else p[0] = v[0];
-}
-
 // Pillow: #define SHIFTFORDIV255(a) ((((a) >> 8) + a) >> 8), PRECISION_BITS 7
 __device__ __forceinline__ uint32_t div255(uint32_t a) { return ((a >> 8) + a) >> 8; }
 
