@@ -267,6 +267,21 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
     }
     return MGR_OK;
   }
+  if constexpr (sizeof(T) == 2) {               // 16-bit: two pixels per thread (composite_only.cuh)
+    const bool ok2 = g.W % 2 == 0 && g.sh % 2 == 0 && g.sc % 2 == 0 && g.sl % 2 == 0 && g.sb % 2 == 0 &&
+                     (reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(gout) |
+                      reinterpret_cast<uintptr_t>(gx)) % 4 == 0;
+    if ((flags & MGR_NEED_GRAD_X) && g.L >= 2 && g.L <= 32 && ok2 && debug_path() != 1) {
+      const long long blocks = ((long long)g.B * g.H * (g.W / 2) + 255) / 256;
+      const unsigned grid = (unsigned)(blocks < 148 * 32 ? blocks : 148 * 32);
+      if (g.L <= 8) composite_bwd_vec2<T, 8><<<grid, 256, 0, s>>>((const T*)x, (const T*)out, (const T*)gout, (T*)gx, g);
+      else if (g.L <= 16) composite_bwd_vec2<T, 16><<<grid, 256, 0, s>>>((const T*)x, (const T*)out, (const T*)gout, (T*)gx, g);
+      else composite_bwd_vec2<T, 32><<<grid, 256, 0, s>>>((const T*)x, (const T*)out, (const T*)gout, (T*)gx, g);
+      MGR_CUDA(cudaGetLastError());
+      count_launch();
+      return MGR_OK;
+    }
+  }
   return launch_backward<T, false>(x, nullptr, out, gout, nullptr, gx, nullptr, g, flags & MGR_NEED_GRAD_X, s);
 }
 

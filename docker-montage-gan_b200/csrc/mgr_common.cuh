@@ -61,6 +61,25 @@ template <int kVec> __device__ __forceinline__ void st_vec_f32(float* p, const f
   else p[0] = v[0];
 }
 
+// two adjacent 16-bit elements: one 32-bit access
+template <> struct VecIO<__nv_bfloat16, 2> {
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, float (&v)[2]) {
+    const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(p));
+    v[0] = __uint_as_float(t << 16); v[1] = __uint_as_float(t & 0xffff0000u);
+  }
+};
+template <> struct VecIO<__half, 2> {
+  static __device__ __forceinline__ void ld(const __half* p, float (&v)[2]) {
+    const uint32_t t = __ldg(reinterpret_cast<const uint32_t*>(p));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&t));
+    v[0] = a.x; v[1] = a.y;
+  }
+};
+__device__ __forceinline__ void st_vec2(__nv_bfloat16* p, const float (&v)[2]) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(v[0], v[1]);
+}
+__device__ __forceinline__ void st_vec2(__half* p, const float (&v)[2]) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(v[0], v[1]); }
+
 template <typename T> __device__ __forceinline__ void st_vec4(T* p, const float (&v)[4]);      // four adjacent elements, aligned
 template <> __device__ __forceinline__ void st_vec4<float>(float* p, const float (&v)[4]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
