@@ -300,6 +300,27 @@ def test_warp_then_composite_equals_render():
     assert (a - b).abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("tf", ["I", "T"])
+def test_warp_then_composite_equals_render_at_config_size(dtype, tol, tf):
+    """256 x 256, L = 7 (config-1/2 geometry): the materialised warp (tiled forward, gather-form backward) followed by the
+    composite-only kernels must reproduce the fused renderer -- output and both gradients."""
+    B, L, H, W = 4, 7, 256, 256
+    x = synth.make_layers(B, L, H, W, "S", seed=31).to(DEV, dtype)
+    th = synth.make_theta(B, L, tf, seed=31).to(DEV)
+    go = synth.make_grad_out(B, H, W, "randn", seed=31).to(DEV, dtype)
+    res = []
+    for two_step in (False, True):
+        xr, tr = x.detach().requires_grad_(True), th.detach().requires_grad_(True)
+        out = mr.render(mr.warp(xr, tr), None) if two_step else mr.render(xr, tr)
+        gx, gt = torch.autograd.grad(out, (xr, tr), go)
+        res.append((out.float(), gx.float(), gt))
+    (o1, gx1, gt1), (o2, gx2, gt2) = res
+    assert (o1 - o2).abs().max().item() < tol
+    assert ((gx1 - gx2).abs().max() / gx1.abs().max()).item() < (1e-4 if dtype == torch.float32 else 2e-2)
+    assert ((gt1 - gt2).abs().max() / gt1.abs().max()).item() < (2e-3 if dtype == torch.float32 else 5e-2)
+
+
 def test_translation_theta_and_known_answers(golden):
     tr = torch.from_numpy(golden["ka/translate2x3/in"]).to(DEV).requires_grad_(True)
     th = mr.convert_translate_to_2x3(tr)
