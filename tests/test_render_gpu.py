@@ -606,3 +606,42 @@ def test_translation_backward_is_deterministic_with_global_gp():
     g0 = run()
     for _ in range(4):
         assert torch.equal(run(), g0)
+
+
+@pytest.mark.parametrize("tf", ["I", "T"])
+def test_forward_and_backward_capture_into_a_cuda_graph(tf):
+    """include/montage_render.h promises stream-ordered calls without allocations or host reads: the C-ABI forward and
+    backward must record into a CUDA graph and replay on new input contents with the results of an eager run."""
+    import ctypes
+    from montage_gan_b200 import _lib
+    lib = _lib.load()
+    B, L, H, W = 4, 7, 64, 64
+    P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    x = synth.make_layers(B, L, H, W, "S", seed=41).to(DEV)
+    th = synth.make_theta(B, L, tf, seed=41).to(DEV)
+    go = synth.make_grad_out(B, H, W, "randn", seed=41).to(DEV)
+    out, gx, gt = torch.empty(B, 4, H, W, device=DEV), torch.empty_like(x), torch.empty(B, L, 2, 3, device=DEV)
+    sav = torch.empty(lib.mgr_saved_alpha_bytes(B, L, H, W, 0), dtype=torch.uint8, device=DEV)
+    wsb = lib.mgr_render_backward_workspace_bytes(B, L, H, W, 0, 1, 3)
+    ws = torch.empty(wsb, dtype=torch.uint8, device=DEV)
+
+    def run(stream):
+        sp = ctypes.c_void_p(stream.cuda_stream)
+        _lib.check(lib.mgr_render_forward(P(x), None, P(th), P(out), P(sav), B, L, H, W, 0, 0, sp), "fwd")
+        _lib.check(lib.mgr_render_backward(P(x), None, P(th), P(out), P(go), P(sav), P(gx), P(gt), P(ws), wsb, B, L, H, W, 0, 0, 3, sp), "bwd")
+
+    run(torch.cuda.current_stream())                                  # warm-up outside capture (function attributes etc.)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        run(torch.cuda.current_stream())
+    # new contents in the same buffers, replay, compare with an eager run on the same contents
+    x.copy_(synth.make_layers(B, L, H, W, "W", seed=42).to(DEV))
+    th.copy_(synth.make_theta(B, L, tf, seed=42).to(DEV))
+    graph.replay()
+    torch.cuda.synchronize()
+    got = (out.clone(), gx.clone(), gt.clone())
+    run(torch.cuda.current_stream())
+    torch.cuda.synchronize()
+    assert torch.equal(got[0], out) and torch.equal(got[1], gx)
+    assert rel_err(got[2].cpu().numpy(), gt.cpu().numpy()) < 1e-5          # atomics: summation order only
