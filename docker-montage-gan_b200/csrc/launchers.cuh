@@ -81,22 +81,13 @@ int launch_forward_tiled(const void* x, const SrcLayers& src, const float* theta
   using Vec = typename Texel<T>::Vec;
   const size_t smem_a = tiled_smem_bytes(g.L, sizeof(Vec)), smem_b = shift_fwd_smem_bytes(g.L, sizeof(Vec));
   const size_t smem = smem_a > smem_b ? smem_a : smem_b;      // one launch serves both code paths (render_fwd.cuh)
-  static bool configured = false;   // per instantiation; attribute is sticky per function
-  if (!configured) {
-    MGR_CUDA(cudaFuncSetAttribute(render_fwd<T, false, kRagged>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    MGR_CUDA(cudaFuncSetAttribute(render_fwd<T, true, kRagged>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    configured = true;
-  }
+  // the forward kernels stay inside the default 48 KB of dynamic shared memory (fp32, L = 32: 45 056 + 2 048 bytes), so no
+  // per-function, per-device opt-in is needed
+  static_assert(sizeof(typename Texel<float>::Vec) * kCapTexels + sizeof(LayerPlan) * kMaxTiledLayers <= 48 * 1024, "forward smem");
   dim3 grid((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B);
   using SA = typename SavedAlpha<T>::type;
   const int stencil = debug_path() != 2;        // all-translation samples take the stencil path
   if constexpr (sizeof(T) == 4) {               // fp32: one launch per path (see render_fwd.cuh)
-    static bool configured32 = false;
-    if (!configured32) {
-      MGR_CUDA(cudaFuncSetAttribute(render_fwd_general_only<T, false, kRagged>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      MGR_CUDA(cudaFuncSetAttribute(render_fwd_general_only<T, true, kRagged>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      configured32 = true;
-    }
     if (sav) render_fwd_general_only<T, true, kRagged><<<grid, kTiledThreads, smem_a, s>>>((const T*)x, src, theta, (T*)out, (SA*)sav, g, stencil);
     else render_fwd_general_only<T, false, kRagged><<<grid, kTiledThreads, smem_a, s>>>((const T*)x, src, theta, (T*)out, nullptr, g, stencil);
     if (stencil) {
@@ -289,11 +280,6 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
 template <typename T>
 int launch_warp_forward(const void* x, const float* theta, void* out, const Geometry& g, cudaStream_t s) {
   if (tiled_ok<T>(x, g)) {                                     // staged footprints, one layer per CTA (warp_tiled.cuh)
-    static bool configured = false;
-    if (!configured) {
-      MGR_CUDA(cudaFuncSetAttribute(warp_fwd_tiled<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-      configured = true;
-    }
     dim3 gridt((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B * g.L);
     warp_fwd_tiled<T><<<gridt, kTiledThreads, sizeof(typename Texel<T>::Vec) * kCapTexels, s>>>((const T*)x, theta, (T*)out, g);
     MGR_CUDA(cudaGetLastError());
