@@ -92,3 +92,26 @@ def test_backward_validation_and_workspace():
     assert rc == 0                                   # nothing requested: no-op
     rc = lib.mgr_render_forward(0x1000, None, None, 0x2000, None, 0, 3, 8, 8, 0, 0, None)
     assert rc == 0                                   # empty batch: no-op
+
+
+def test_new_entry_points_validate_before_touching_memory():
+    """mgr_composite_u8, the ragged pair and mgr_warp_backward: argument errors come back as codes with a message
+    (no GPU needed: every call below fails validation or is an empty batch)."""
+    import ctypes
+    lib = _lib.load()
+    assert lib.mgr_composite_u8(0x1000, None, None, None, 2, 3, 8, 8, 0, 0, None) == 1 and b"both NULL" in lib.mgr_last_error()
+    assert lib.mgr_composite_u8(0x1000, None, 0x2000, None, 0, 3, 8, 8, 0, 0, None) == 0            # empty batch
+    assert lib.mgr_composite_u8(0x1000, None, 0x2000, None, 2, 3, 8, 8, 7, 0, None) == 1            # bad dtype
+    lay = (_lib.MgrLayer * 2)(_lib.MgrLayer(0x1000, 4 * 64, 64, 8, 8, 8, 0, 0), _lib.MgrLayer(0x9000, 4 * 16, 16, 4, 4, 4, 2, 2))
+    assert lib.mgr_render_forward_ragged(lay, None, 0x2000, None, 2, 2, 8, 8, 0, 0, None) == 2 and b"theta" in lib.mgr_last_error()
+    assert lib.mgr_render_forward_ragged(None, 0x3000, 0x2000, None, 2, 2, 8, 8, 0, 0, None) == 1
+    assert lib.mgr_render_forward_ragged(lay, 0x3000, 0x2000, None, 2, 1, 8, 8, 0, 0, None) == 2     # a ragged stack needs >= 2 layers
+    assert lib.mgr_render_forward_ragged(lay, 0x3000, 0x2000, None, 0, 2, 8, 8, 0, 0, None) == 0     # empty batch
+    assert lib.mgr_render_forward_ragged(lay, 0x3000, 0x2000, None, 2, 2, 8, 8, 0, 0, None) == 2     # left offset 2: not a multiple of 4
+    assert b"multiples of 4" in lib.mgr_last_error()
+    assert lib.mgr_render_backward_ragged(lay, 0x3000, 0x2000, 0x2000, 0x4000, lay, 0x5000, None, 0, 2, 2, 8, 8, 0, 0, 3, None) == 3
+    assert b"workspace" in lib.mgr_last_error()
+    need = lib.mgr_warp_backward_workspace_bytes(2, 3, 8, 8, _lib.MGR_F32, 3)
+    assert need == 2 * 3 * (128 + 4 + 4) + 32 + 2 * 4                                                 # gather path bookkeeping
+    assert lib.mgr_warp_backward_workspace_bytes(2, 3, 8, 8, _lib.MGR_BF16, 1) == 2 * 3 * 4 * 64 * 4  # fp32 scatter accumulator dominates
+    assert lib.mgr_warp_backward(0x1000, None, 0x3000, 0x2000, 0x4000, 0x5000, None, 0, 2, 3, 8, 8, 0, 0, 3, None) == 3

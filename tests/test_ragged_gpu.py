@@ -88,7 +88,7 @@ def test_ragged_parity_vs_oracle_on_padded_canvas(canvas, sizes, tf):
 
 @pytest.mark.parametrize("canvas,sizes", CASES + [((256, 256), REFERENCE_SIZES)])
 @pytest.mark.parametrize("tf", ["I", "T"])
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16, torch.float16])
 def test_ragged_equals_canvas_path_on_padded_tensor(canvas, sizes, tf, dtype):
     B, L = 2, len(sizes)
     layers, padded = _make(B, canvas, sizes, "F" if dtype == torch.float32 else "S", seed=5, dtype=dtype)
