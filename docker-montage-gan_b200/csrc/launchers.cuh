@@ -168,14 +168,21 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
   int* wcnt = work + (size_t)g.B * g.L;                                  // [0] layers in the work list
   int* sflag = wcnt + 2;                                                 // [B] sample is all translations
   if ((long long)g.B * g.L > 65535) return fail(MGR_ERR_UNSUPPORTED, "B*L=%lld exceeds 65535 per backward call; split the batch", (long long)g.B * g.L);
-  if (nt) MGR_CUDA(cudaMemsetAsync(gtheta, 0, sizeof(float) * 6 * g.B * g.L, s));
   // placements first: inverse plans + launch order for pass 2, and the per-sample "all translations" flags every
   // kernel below uses to claim or decline a sample with one load
-  MGR_CUDA(cudaMemsetAsync(order + g.B * g.L, 0, 2 * sizeof(int), s));
-  inverse_plans_kernel<<<(g.B * g.L + 127) / 128, 128, 0, s>>>(theta, inv, g.B * g.L, g.H, g.W, order, order + g.B * g.L);
-  sample_flags_kernel<<<1, 256, 0, s>>>(inv, g.B, g.L, order, work, wcnt, sflag, debug_path() != 2);
-  MGR_CUDA(cudaGetLastError());
-  count_launch(2);
+  if (g.B * g.L <= kSmallPlacements) {
+    placements_small_kernel<<<1, 256, 0, s>>>(theta, inv, g.B, g.L, g.H, g.W, order, work, wcnt, sflag, nt ? gtheta : nullptr,
+                                              debug_path() != 2);
+    MGR_CUDA(cudaGetLastError());
+    count_launch();
+  } else {
+    if (nt) MGR_CUDA(cudaMemsetAsync(gtheta, 0, sizeof(float) * 6 * g.B * g.L, s));
+    MGR_CUDA(cudaMemsetAsync(order + g.B * g.L, 0, 2 * sizeof(int), s));
+    inverse_plans_kernel<<<(g.B * g.L + 127) / 128, 128, 0, s>>>(theta, inv, g.B * g.L, g.H, g.W, order, order + g.B * g.L);
+    sample_flags_kernel<<<1, 256, 0, s>>>(inv, g.B, g.L, order, work, wcnt, sflag, debug_path() != 2);
+    MGR_CUDA(cudaGetLastError());
+    count_launch(2);
+  }
   size_t smem = align16(tiled_smem_bytes(g.L, sizeof(Vec))) +
                 sizeof(float) * (size_t)g.L * kPx * kTiledThreads;                // + transmittance stash
   // (G_P, G_A) copy in shared memory if two CTAs per SM still fit (the kernels are compiled for two: at three they
@@ -307,11 +314,17 @@ int launch_warp_backward(const void* x, const float* theta, const void* gout, vo
     int* wcnt = work + (size_t)g.B * g.L;
     int* sflag = wcnt + 2;
     if (nx) {
-      MGR_CUDA(cudaMemsetAsync(order + g.B * g.L, 0, 2 * sizeof(int), s));
-      inverse_plans_kernel<<<(g.B * g.L + 127) / 128, 128, 0, s>>>(theta, inv, g.B * g.L, g.H, g.W, order, order + g.B * g.L);
-      sample_flags_kernel<<<1, 256, 0, s>>>(inv, g.B, g.L, order, work, wcnt, sflag, 0);      // every layer stays in the work list
-      MGR_CUDA(cudaGetLastError());
-      count_launch(2);
+      if (g.B * g.L <= kSmallPlacements) {                       // every layer stays in the work list (skip_shift = 0)
+        placements_small_kernel<<<1, 256, 0, s>>>(theta, inv, g.B, g.L, g.H, g.W, order, work, wcnt, sflag, nullptr, 0);
+        MGR_CUDA(cudaGetLastError());
+        count_launch();
+      } else {
+        MGR_CUDA(cudaMemsetAsync(order + g.B * g.L, 0, 2 * sizeof(int), s));
+        inverse_plans_kernel<<<(g.B * g.L + 127) / 128, 128, 0, s>>>(theta, inv, g.B * g.L, g.H, g.W, order, order + g.B * g.L);
+        sample_flags_kernel<<<1, 256, 0, s>>>(inv, g.B, g.L, order, work, wcnt, sflag, 0);
+        MGR_CUDA(cudaGetLastError());
+        count_launch(2);
+      }
       const long long blocks = (long long)((g.W + 31) / 32) * ((g.H + 31) / 32) * g.B * g.L;
       if (blocks >= 16384) {
         dim3 grid2((g.W + 31) / 32, (g.H + 31) / 32, g.B * g.L);

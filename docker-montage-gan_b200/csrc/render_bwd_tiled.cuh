@@ -261,11 +261,8 @@ static_assert(sizeof(InverseLayer) <= 128, "workspace reserves 128 B per layer p
 // near-singular placements, a few hundred candidates per texel) are scheduled FIRST so that their long-running
 // blocks overlap the rest of the grid instead of forming a tail (longest-processing-time-first).
 // order[0..n): heavy layers from the front, the others from the back; cnt[2] zeroed by the caller.
-static __global__ void inverse_plans_kernel(const float* __restrict__ theta, InverseLayer* __restrict__ plans, int n, int H, int W,
-                                            int* __restrict__ order, int* __restrict__ cnt) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n) return;
-  const float* th = theta + (long long)k * 6;
+// the inverse placement of one layer; heavy: its per-texel window is huge (scheduled first by pass 2)
+__device__ __forceinline__ InverseLayer make_inverse_plan(const float* __restrict__ th, int H, int W, bool& heavy) {
   const double w = W, h = H;
   const double a00 = th[0], a01 = th[1] * (w / h), a10 = th[3] * (h / w), a11 = th[4];
   InverseLayer q;
@@ -281,14 +278,24 @@ static __global__ void inverse_plans_kernel(const float* __restrict__ theta, Inv
   q.r00 = fabs(a00) > 1e-6 ? (float)(1.0 / a00) : 0.f;
   q.r10 = fabs(a10) > 1e-6 ? (float)(1.0 / a10) : 0.f;
   q.wide = (2.0 * rj > 3.5) || (2.0 * ri > 3.5);
-  const bool heavy = q.valid && fmin(rj, (double)W) * fmin(ri, (double)H) > 64.0;
-  if (heavy) order[atomicAdd(&cnt[0], 1)] = k;
-  else order[n - 1 - atomicAdd(&cnt[1], 1)] = k;
+  heavy = q.valid && fmin(rj, (double)W) * fmin(ri, (double)H) > 64.0;
   // what STNv2c emits (convert_translate_to_2x3, image_utils.py:316-335): the adjoint is a fixed 2x2 stencil
   q.shift_only = is_pure_shift(th);
   const double fX = floor(q.c0), fY = floor(q.c1);
   q.X = q.shift_only ? (int)fX : 0; q.Y = q.shift_only ? (int)fY : 0;
   q.fx = q.shift_only ? (float)(q.c0 - fX) : 0.f; q.fy = q.shift_only ? (float)(q.c1 - fY) : 0.f;
+  q.all_shift = 0;
+  return q;
+}
+
+static __global__ void inverse_plans_kernel(const float* __restrict__ theta, InverseLayer* __restrict__ plans, int n, int H, int W,
+                                            int* __restrict__ order, int* __restrict__ cnt) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  bool heavy;
+  const InverseLayer q = make_inverse_plan(theta + (long long)k * 6, H, W, heavy);
+  if (heavy) order[atomicAdd(&cnt[0], 1)] = k;
+  else order[n - 1 - atomicAdd(&cnt[1], 1)] = k;
   plans[k] = q;
 }
 
@@ -296,9 +303,9 @@ static __global__ void inverse_plans_kernel(const float* __restrict__ theta, Inv
 // render_bwd_shift).  Phase 2: the layers pass 2 has to process, in launch order (order[] minus the layers of
 // all-translation samples when the stencil kernels are on), compacted into work[0 .. wcnt[0]).  A batch of
 // translations leaves pass 2 with nothing to do.
-static __global__ void __launch_bounds__(256)
-sample_flags_kernel(InverseLayer* __restrict__ plans, int B, int L, const int* __restrict__ order, int* __restrict__ work,
-                    int* __restrict__ wcnt, int* __restrict__ sample_all_shift, int skip_shift) {
+__device__ __forceinline__ void sample_flags_cta(InverseLayer* __restrict__ plans, int B, int L, const int* __restrict__ order,
+                                                 int* __restrict__ work, int* __restrict__ wcnt, int* __restrict__ sample_all_shift,
+                                                 int skip_shift) {
   __shared__ int s_warp[8], s_base;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int b = tid; b < B; b += 256) {
@@ -329,6 +336,39 @@ sample_flags_kernel(InverseLayer* __restrict__ plans, int B, int L, const int* _
     __syncthreads();
   }
   if (tid == 0) { wcnt[0] = s_base; wcnt[1] = 0; }
+}
+
+static __global__ void __launch_bounds__(256)
+sample_flags_kernel(InverseLayer* __restrict__ plans, int B, int L, const int* __restrict__ order, int* __restrict__ work,
+                    int* __restrict__ wcnt, int* __restrict__ sample_all_shift, int skip_shift) {
+  sample_flags_cta(plans, B, L, order, work, wcnt, sample_all_shift, skip_shift);
+}
+
+// Both steps in ONE single-CTA launch for batches of up to kSmallPlacements layers (every configuration of the
+// reference): placements, launch order (counters in shared memory, so no memset), flags, work list, and -- if asked --
+// the zeroing of grad_theta.  Four tiny launches become one; they sit on the critical path in front of pass 1.
+constexpr int kSmallPlacements = 1024;
+static __global__ void __launch_bounds__(256)
+placements_small_kernel(const float* __restrict__ theta, InverseLayer* __restrict__ plans, int B, int L, int H, int W,
+                        int* __restrict__ order, int* __restrict__ work, int* __restrict__ wcnt, int* __restrict__ sample_all_shift,
+                        float* __restrict__ gtheta_to_zero, int skip_shift) {
+  __shared__ int s_cnt[2];
+  const int n = B * L;
+  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (int k = threadIdx.x; k < n; k += 256) {
+    bool heavy;
+    const InverseLayer q = make_inverse_plan(theta + (long long)k * 6, H, W, heavy);
+    if (heavy) order[atomicAdd(&s_cnt[0], 1)] = k;
+    else order[n - 1 - atomicAdd(&s_cnt[1], 1)] = k;
+    plans[k] = q;
+    if (gtheta_to_zero) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) gtheta_to_zero[(long long)k * 6 + c] = 0.f;
+    }
+  }
+  __syncthreads();                              // plans and order are visible to the whole CTA
+  sample_flags_cta(plans, B, L, order, work, wcnt, sample_all_shift, skip_shift);
 }
 
 // Block of 256 threads = 32 x 8 threads, each owning a 2 x 2 block of texels -> 64 x 16 texels per CTA.
