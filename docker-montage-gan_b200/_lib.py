@@ -51,6 +51,9 @@ SYMBOLS = {
     "mgr_composite_jvp": (_i, [_vp, _i64p, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mgr_render_forward_ragged": (_i, [_layp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mgr_render_backward_ragged": (_i, [_layp, _vp, _vp, _vp, _vp, _layp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "mgr_augment_geom_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i, _i]),
+    "mgr_augment_geom_forward": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "mgr_augment_geom_backward": (_i, [_vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "mgr_composite_u8": (_i, [_vp, _i64p, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mgr_render_host_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "mgr_render_fwd_bwd_host": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -11,6 +11,7 @@
 #include "warp_ops.cuh"
 
 #include "launchers_decl.h"
+#include "augment_geom.cuh"
 
 namespace {
 thread_local char g_err[512] = "";
@@ -308,6 +309,77 @@ int mgr_composite_u8(const void* x, const int64_t* x_strides, float* out_f32, un
     case MGR_BF16: return mgr_pil_bf16(x, out_f32, out_u8, g, s);
     default: return mgr_pil_f16(x, out_f32, out_u8, g, s);
   }
+}
+
+// ---- AugmentPipe's geometric execution block (augment_geom.cuh) ------------------------------------------------
+namespace {
+int aug_geometry(int B, int C, int H, int W, int mx0, int my0, int mx1, int my1, mgr::AugGeom* a) {
+  if (B < 0 || C < 1 || H < 2 || W < 2) return fail(MGR_ERR_INVALID_ARGUMENT, "bad shape B=%d C=%d H=%d W=%d", B, C, H, W);
+  if (mx0 < 0 || mx1 < 0 || my0 < 0 || my1 < 0 || mx0 > W - 1 || mx1 > W - 1 || my0 > H - 1 || my1 > H - 1)
+    return fail(MGR_ERR_INVALID_ARGUMENT, "reflect margins (%d,%d,%d,%d) must lie in [0, size - 1]", mx0, my0, mx1, my1);
+  a->B = B; a->C = C; a->H = H; a->W = W;
+  a->mx0 = mx0; a->my0 = my0; a->mx1 = mx1; a->my1 = my1;
+  a->Hp = H + my0 + my1; a->Wp = W + mx0 + mx1;
+  a->Hu = 2 * a->Hp; a->Wu = 2 * a->Wp;
+  a->Hs = 2 * (H + 6); a->Ws = 2 * (W + 6);
+  if ((long long)B * C * a->Hu * a->Wu >= (1LL << 40)) return fail(MGR_ERR_UNSUPPORTED, "problem too large");
+  return MGR_OK;
+}
+unsigned aug_grid(long long total) {
+  const long long blocks = (total + 255) / 256;
+  return (unsigned)(blocks < 148 * 32 ? (blocks > 0 ? blocks : 1) : 148 * 32);
+}
+}  // namespace
+
+size_t mgr_augment_geom_workspace_bytes(int B, int C, int H, int W, int mx0, int my0, int mx1, int my1) {
+  mgr::AugGeom a;
+  if (aug_geometry(B, C, H, W, mx0, my0, mx1, my1, &a) != MGR_OK) return 0;
+  const size_t bc = (size_t)B * C;
+  return sizeof(float) * bc * ((size_t)a.Hu * a.Wu + (size_t)a.Hs * a.Ws + (size_t)a.Hp * a.Wp);
+}
+
+int mgr_augment_geom_forward(const float* images, const float* theta, float* out, void* workspace, size_t workspace_bytes,
+                             int B, int C, int H, int W, int mx0, int my0, int mx1, int my1, void* stream) {
+  mgr::AugGeom a;
+  if (int rc = aug_geometry(B, C, H, W, mx0, my0, mx1, my1, &a)) return rc;
+  if (!images || !theta || !out) return fail(MGR_ERR_INVALID_ARGUMENT, "images / theta / out is NULL");
+  if (B == 0) return MGR_OK;
+  const size_t need = mgr_augment_geom_workspace_bytes(B, C, H, W, mx0, my0, mx1, my1);
+  if (!workspace || workspace_bytes < need) return fail(MGR_ERR_WORKSPACE_TOO_SMALL, "workspace %zu bytes < required %zu", workspace_bytes, need);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long bc = (long long)B * C;
+  float* U = (float*)workspace;
+  float* S = U + bc * a.Hu * a.Wu;
+  mgr::aug_up_fwd<<<aug_grid(bc * a.Hu * a.Wu), 256, 0, s>>>(images, U, a);
+  mgr::aug_sample<false><<<aug_grid((long long)B * a.Hs * a.Ws), 256, 0, s>>>(theta, U, S, a);
+  mgr::aug_down_fwd<<<aug_grid(bc * H * W), 256, 0, s>>>(S, out, a);
+  MGR_CUDA(cudaGetLastError());
+  mgr::count_launch(3);
+  return MGR_OK;
+}
+
+int mgr_augment_geom_backward(const float* grad_out, const float* theta, float* grad_images, void* workspace,
+                              size_t workspace_bytes, int B, int C, int H, int W, int mx0, int my0, int mx1, int my1,
+                              void* stream) {
+  mgr::AugGeom a;
+  if (int rc = aug_geometry(B, C, H, W, mx0, my0, mx1, my1, &a)) return rc;
+  if (!grad_out || !theta || !grad_images) return fail(MGR_ERR_INVALID_ARGUMENT, "grad_out / theta / grad_images is NULL");
+  if (B == 0) return MGR_OK;
+  const size_t need = mgr_augment_geom_workspace_bytes(B, C, H, W, mx0, my0, mx1, my1);
+  if (!workspace || workspace_bytes < need) return fail(MGR_ERR_WORKSPACE_TOO_SMALL, "workspace %zu bytes < required %zu", workspace_bytes, need);
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long bc = (long long)B * C;
+  float* gU = (float*)workspace;
+  float* gS = gU + bc * a.Hu * a.Wu;
+  float* gxp = gS + bc * a.Hs * a.Ws;
+  mgr::aug_down_bwd<<<aug_grid(bc * a.Hs * a.Ws), 256, 0, s>>>(grad_out, gS, a);
+  MGR_CUDA(cudaMemsetAsync(gU, 0, sizeof(float) * bc * a.Hu * a.Wu, s));
+  mgr::aug_sample<true><<<aug_grid((long long)B * a.Hs * a.Ws), 256, 0, s>>>(theta, gS, gU, a);
+  mgr::aug_up_bwd_padded<<<aug_grid(bc * a.Hp * a.Wp), 256, 0, s>>>(gU, gxp, a);
+  mgr::aug_fold_reflect<<<aug_grid(bc * H * W), 256, 0, s>>>(gxp, grad_images, a);
+  MGR_CUDA(cudaGetLastError());
+  mgr::count_launch(4);
+  return MGR_OK;
 }
 
 // ---- end-to-end entry point with HOST buffers: chunked, double-buffered, three streams ----------------

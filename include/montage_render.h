@@ -200,6 +200,22 @@ int mgr_composite_u8(const void* x, const int64_t* x_strides, float* out_f32, un
                      int B, int L, int H, int W, int dtype, int range_mode, void* stream);
 
 /*
+ * AugmentPipe's geometric execution block (training/augment.py:306-342): reflect pad by the margins,
+ * x2 upsample with the sym6 low-pass, affine bilinear resampling onto a 2(H+6) x 2(W+6) grid, low-pass + x2 decimation
+ * + crop back to H x W.  fp32, contiguous [B,C,H,W].  The caller supplies what the reference computes on the host:
+ *   mx0, my0, mx1, my1  the reflect padding (augment.py:311-322), each in [0, size - 1]
+ *   theta [B,2,3]       device pointer: the matrices the reference hands to affine_grid (augment.py:326-338)
+ * (montage_gan_b200.augment.geometric_warp derives both from G_inv).  The backward is the adjoint chain (the block is
+ * linear in the images): grad_images is written completely.  workspace: mgr_augment_geom_workspace_bytes(...) bytes.
+ */
+size_t mgr_augment_geom_workspace_bytes(int B, int C, int H, int W, int mx0, int my0, int mx1, int my1);
+int mgr_augment_geom_forward(const float* images, const float* theta, float* out, void* workspace, size_t workspace_bytes,
+                             int B, int C, int H, int W, int mx0, int my0, int mx1, int my1, void* stream);
+int mgr_augment_geom_backward(const float* grad_out, const float* theta, float* grad_images, void* workspace,
+                              size_t workspace_bytes, int B, int C, int H, int W, int mx0, int my0, int mx1, int my1,
+                              void* stream);
+
+/*
  * End to end with HOST buffers: out, grad_x, grad_theta = fwd+bwd(x, theta, grad_out), everything in
  * (preferably pinned) host memory, laid out exactly like the device tensors.  The batch is cut
  * into chunks of chunk_B samples that flow through two device slots on three streams (H2D copy,

@@ -51,3 +51,54 @@ def test_oracle_filters_known_answers():
     xs = torch.nn.functional.avg_pool2d(x, 5, 1, 2)                     # a smooth image survives the low-pass
     y = AG.geometric_warp(xs, torch.eye(3)[None])
     assert float((y - xs)[:, :, 4:-4, 4:-4].abs().max()) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------ GPU
+@pytest.mark.gpu
+def test_cuda_matches_reference_golden(golden):
+    from montage_gan_b200 import augment as A
+    for n in [str(v) for v in golden["names"]]:
+        x, Gi = torch.from_numpy(golden[f"{n}/images"]).cuda(), torch.from_numpy(golden[f"{n}/G_inv"])
+        assert A.padding_margins(Gi, x.shape[2], x.shape[3]) == tuple(int(v) for v in golden[f"{n}/margins"]), n
+        y = A.geometric_warp(x, Gi)
+        assert y.shape == x.shape
+        err = float((y.cpu() - torch.from_numpy(golden[f"{n}/out"])).abs().max())
+        assert err < 5e-5, (n, err)                                     # fp32 round-off of the sampling coordinates
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shape", [(2, 4, 64, 64), (1, 3, 40, 56), (3, 4, 33, 47)])
+def test_cuda_forward_and_gradient_match_oracle(shape):
+    from montage_gan_b200 import augment as A
+    B, C, H, W = shape
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand(shape, generator=g) * 2 - 1
+    ang = (torch.rand(B, generator=g) - 0.5) * 1.5
+    sc = 0.8 + 0.5 * torch.rand(B, generator=g)
+    Gi = torch.eye(3).repeat(B, 1, 1)
+    Gi[:, 0, 0], Gi[:, 0, 1] = sc * torch.cos(ang), -sc * torch.sin(ang) * 1.1
+    Gi[:, 1, 0], Gi[:, 1, 1] = sc * torch.sin(ang), sc * torch.cos(ang) * 0.9
+    Gi[:, 0, 2], Gi[:, 1, 2] = (torch.rand(B, generator=g) - 0.5) * 0.3 * W, (torch.rand(B, generator=g) - 0.5) * 0.3 * H
+    go = torch.randn(shape, generator=g)
+    xr = x.clone().requires_grad_(True)
+    ref = AG.geometric_warp(xr, Gi)
+    (gref,) = torch.autograd.grad(ref, xr, go)
+    xd = x.cuda().requires_grad_(True)
+    out = A.geometric_warp(xd, Gi)
+    (gd,) = torch.autograd.grad(out, xd, go.cuda())
+    assert float((out.detach().cpu() - ref.detach()).abs().max()) < 5e-5
+    assert float((gd.cpu() - gref).abs().max() / gref.abs().max()) < 1e-4
+
+
+@pytest.mark.gpu
+def test_cuda_argument_rules():
+    from montage_gan_b200 import _lib, augment as A
+    x = torch.zeros(1, 4, 16, 16, device="cuda")
+    with pytest.raises(ValueError):
+        A.geometric_warp(x.half(), torch.eye(3))
+    with pytest.raises(ValueError):
+        A.geometric_warp(x, torch.eye(3).repeat(2, 1, 1))
+    with pytest.raises(_lib.MontageRenderError):
+        A.geometric_warp(x.cpu(), torch.eye(3))
+    y = A.geometric_warp(x + 0.25, torch.eye(3))                        # identity transform of a constant image
+    assert float((y - 0.25).abs().max()) < 1e-5
