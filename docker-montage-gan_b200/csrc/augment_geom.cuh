@@ -25,30 +25,52 @@ struct AugGeom {
 
 __device__ __forceinline__ int reflect_index(int p, int n) { return p < 0 ? -p : (p >= n ? 2 * (n - 1) - p : p); }
 
-// U[Y, X] = sum_k sum_l g[k] g[l] u0[Y + k - 6, X + l - 6],  g = 2 * flip(f),  u0[2i, 2j] = reflect-padded image, else 0
+// Every FIR stage is separable (upfirdn2d.py:211-216 runs two 1-D convolutions as well): one kernel per axis, a thread
+// per output element, the intermediate in the workspace.  n_out / n_in are the lengths along the filtered axis; the
+// other axis has `other` elements; kAlongX selects which of the two innermost axes is filtered.
+//   kUp:       dst[X] = sum_{k = X mod 2, step 2} g[k] src[reflect((X + k - 6) / 2 - m0)],  g = 2 flip(f)   (x2 upsample of
+//              the reflect-padded signal; zeros between samples never get multiplied)
+//   kDown:     dst[x] = sum_k f[k] src[2 x + k + 1]                                          (crop 1, correlate, decimate)
+//   kDownAdj:  dst[X] = sum_{k: X - 1 - k even} f[k] src[(X - 1 - k) / 2]                    (adjoint of kDown)
+//   kUpAdj:    dst[j] = sum_k g[k] src[2 j + 6 - k]            (adjoint of kUp w.r.t. the PADDED signal; fold follows)
+enum { kUp = 0, kDown = 1, kDownAdj = 2, kUpAdj = 3 };
+template <int kOp, bool kAlongX>
 static __global__ void __launch_bounds__(256)
-aug_up_fwd(const float* __restrict__ img, float* __restrict__ U, AugGeom a) {
-  const long long total = (long long)a.B * a.C * a.Hu * a.Wu;
+aug_fir_1d(const float* __restrict__ src, float* __restrict__ dst, long long planes, int n_in, int n_out, int other, int m0) {
+  // layout: [planes][rows][cols]; kAlongX: rows = other, cols filtered; else rows filtered, cols = other
+  const int cols_out = kAlongX ? n_out : other, rows_out = kAlongX ? other : n_out;
+  const int cols_in = kAlongX ? n_in : other, rows_in = kAlongX ? other : n_in;
+  const long long total = planes * rows_out * cols_out;
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
-    const int X = (int)(k % a.Wu), Y = (int)((k / a.Wu) % a.Hu);
-    const long long bc = k / ((long long)a.Wu * a.Hu);
-    const float* p = img + bc * a.H * a.W;
+    const int c = (int)(k % cols_out), r = (int)((k / cols_out) % rows_out);
+    const long long pl = k / ((long long)cols_out * rows_out);
+    const int o = kAlongX ? c : r;                             // position along the filtered axis
+    const float* p = src + pl * rows_in * cols_in + (kAlongX ? (long long)r * cols_in : c);
+    const int step = kAlongX ? 1 : cols_in;
     float acc = 0.f;
-    for (int ky = Y & 1; ky < kFir; ky += 2) {                   // taps that land on an even (= non-zero) row
-      const int ty = Y + ky - 6;
-      if (ty < 0 || ty >= a.Hu) continue;
-      const int iy = reflect_index((ty >> 1) - a.my0, a.H);
-      const float gy = 2.f * c_sym6[kFir - 1 - ky];
-      float row = 0.f;
-      for (int kx = X & 1; kx < kFir; kx += 2) {
-        const int tx = X + kx - 6;
-        if (tx < 0 || tx >= a.Wu) continue;
-        const int ix = reflect_index((tx >> 1) - a.mx0, a.W);
-        row = fmaf(2.f * c_sym6[kFir - 1 - kx], p[iy * a.W + ix], row);
+    if (kOp == kUp) {
+      for (int t = o & 1; t < kFir; t += 2) {
+        const int u = o + t - 6;                               // position in the zero-inserted padded signal (even here)
+        if (u < 0 || u >= n_out) continue;
+        acc = fmaf(2.f * c_sym6[kFir - 1 - t], p[(long long)reflect_index((u >> 1) - m0, n_in) * step], acc);
       }
-      acc = fmaf(gy, row, acc);
+    } else if (kOp == kDown) {
+#pragma unroll
+      for (int t = 0; t < kFir; ++t) acc = fmaf(c_sym6[t], p[(long long)(2 * o + t + 1) * step], acc);
+    } else if (kOp == kDownAdj) {
+      for (int t = (o - 1) & 1; t < kFir; t += 2) {
+        const int x2 = o - 1 - t;
+        if (x2 < 0 || (x2 >> 1) >= n_in) continue;
+        acc = fmaf(c_sym6[t], p[(long long)(x2 >> 1) * step], acc);
+      }
+    } else {
+      for (int t = 0; t < kFir; ++t) {
+        const int X = 2 * o + 6 - t;
+        if (X < 0 || X >= n_in) continue;
+        acc = fmaf(2.f * c_sym6[kFir - 1 - t], p[(long long)X * step], acc);
+      }
     }
-    U[k] = acc;
+    dst[k] = acc;
   }
 }
 
@@ -97,75 +119,7 @@ aug_sample(const float* __restrict__ theta, const float* __restrict__ src, float
   }
 }
 
-// out[y, x] = sum_k sum_l f[k] f[l] S[2 y + k + 1, 2 x + l + 1]      (crop 1, correlate, keep every second sample)
-static __global__ void __launch_bounds__(256)
-aug_down_fwd(const float* __restrict__ S, float* __restrict__ out, AugGeom a) {
-  const long long total = (long long)a.B * a.C * a.H * a.W;
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(k % a.W), y = (int)((k / a.W) % a.H);
-    const long long bc = k / ((long long)a.W * a.H);
-    const float* p = S + bc * a.Hs * a.Ws + (long long)(2 * y + 1) * a.Ws + (2 * x + 1);
-    float acc = 0.f;
-    for (int ky = 0; ky < kFir; ++ky) {
-      float row = 0.f;
-#pragma unroll
-      for (int kx = 0; kx < kFir; ++kx) row = fmaf(c_sym6[kx], p[ky * a.Ws + kx], row);
-      acc = fmaf(c_sym6[ky], row, acc);
-    }
-    out[k] = acc;
-  }
-}
-
-// adjoint of aug_down_fwd: gS[Y, X] = sum over (y, k): 2 y + k + 1 = Y, (x, l): 2 x + l + 1 = X of f[k] f[l] gout[y, x]
-static __global__ void __launch_bounds__(256)
-aug_down_bwd(const float* __restrict__ gout, float* __restrict__ gS, AugGeom a) {
-  const long long total = (long long)a.B * a.C * a.Hs * a.Ws;
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
-    const int X = (int)(k % a.Ws), Y = (int)((k / a.Ws) % a.Hs);
-    const long long bc = k / ((long long)a.Ws * a.Hs);
-    const float* p = gout + bc * a.H * a.W;
-    float acc = 0.f;
-    for (int ky = (Y - 1) & 1; ky < kFir; ky += 2) {             // 2 y = Y - 1 - ky must be even and inside
-      const int y2 = Y - 1 - ky;
-      if (y2 < 0 || (y2 >> 1) >= a.H) continue;
-      float row = 0.f;
-      for (int kx = (X - 1) & 1; kx < kFir; kx += 2) {
-        const int x2 = X - 1 - kx;
-        if (x2 < 0 || (x2 >> 1) >= a.W) continue;
-        row = fmaf(c_sym6[kx], p[(y2 >> 1) * a.W + (x2 >> 1)], row);
-      }
-      acc = fmaf(c_sym6[ky], row, acc);
-    }
-    gS[k] = acc;
-  }
-}
-
-// adjoint of aug_up_fwd, first half: gradient w.r.t. the reflect-PADDED image,
-//   gxp[i, j] = sum_k sum_l g[k] g[l] gU[2 i + 6 - k, 2 j + 6 - l]
-static __global__ void __launch_bounds__(256)
-aug_up_bwd_padded(const float* __restrict__ gU, float* __restrict__ gxp, AugGeom a) {
-  const long long total = (long long)a.B * a.C * a.Hp * a.Wp;
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(k % a.Wp), i = (int)((k / a.Wp) % a.Hp);
-    const long long bc = k / ((long long)a.Wp * a.Hp);
-    const float* p = gU + bc * a.Hu * a.Wu;
-    float acc = 0.f;
-    for (int ky = 0; ky < kFir; ++ky) {
-      const int Y = 2 * i + 6 - ky;
-      if (Y < 0 || Y >= a.Hu) continue;
-      float row = 0.f;
-      for (int kx = 0; kx < kFir; ++kx) {
-        const int X = 2 * j + 6 - kx;
-        if (X < 0 || X >= a.Wu) continue;
-        row = fmaf(2.f * c_sym6[kFir - 1 - kx], p[(long long)Y * a.Wu + X], row);
-      }
-      acc = fmaf(2.f * c_sym6[kFir - 1 - ky], row, acc);
-    }
-    gxp[k] = acc;
-  }
-}
-
-// second half: fold the reflect padding back, gimg[y, x] = sum of gxp over the padded positions that mirror onto (y, x)
+// fold the reflect padding back after the kUpAdj passes, gimg[y, x] = sum of gxp over the padded positions that mirror onto (y, x)
 __device__ __forceinline__ int reflect_sources(int x, int n, int m0, int m1, int (&src)[3]) {
   int cnt = 0;
   src[cnt++] = x + m0;                                          // the pixel itself

@@ -325,6 +325,13 @@ int aug_geometry(int B, int C, int H, int W, int mx0, int my0, int mx1, int my1,
   if ((long long)B * C * a->Hu * a->Wu >= (1LL << 40)) return fail(MGR_ERR_UNSUPPORTED, "problem too large");
   return MGR_OK;
 }
+// intermediate of the separable FIR stages, per (b, c) plane: rows x cols of the half-filtered signal
+size_t aug_temp_elems(const mgr::AugGeom& a) {
+  size_t m = (size_t)a.H * a.Wu;                               // upsample: along x first
+  if ((size_t)a.Hs * a.W > m) m = (size_t)a.Hs * a.W;          // decimation (and its adjoint): x of the tall signal
+  if ((size_t)a.Hu * a.Wp > m) m = (size_t)a.Hu * a.Wp;        // adjoint of the upsample: along x first
+  return m;
+}
 unsigned aug_grid(long long total) {
   const long long blocks = (total + 255) / 256;
   return (unsigned)(blocks < 148 * 32 ? (blocks > 0 ? blocks : 1) : 148 * 32);
@@ -335,7 +342,7 @@ size_t mgr_augment_geom_workspace_bytes(int B, int C, int H, int W, int mx0, int
   mgr::AugGeom a;
   if (aug_geometry(B, C, H, W, mx0, my0, mx1, my1, &a) != MGR_OK) return 0;
   const size_t bc = (size_t)B * C;
-  return sizeof(float) * bc * ((size_t)a.Hu * a.Wu + (size_t)a.Hs * a.Ws + (size_t)a.Hp * a.Wp);
+  return sizeof(float) * bc * ((size_t)a.Hu * a.Wu + (size_t)a.Hs * a.Ws + (size_t)a.Hp * a.Wp + aug_temp_elems(a));
 }
 
 int mgr_augment_geom_forward(const float* images, const float* theta, float* out, void* workspace, size_t workspace_bytes,
@@ -350,11 +357,17 @@ int mgr_augment_geom_forward(const float* images, const float* theta, float* out
   const long long bc = (long long)B * C;
   float* U = (float*)workspace;
   float* S = U + bc * a.Hu * a.Wu;
-  mgr::aug_up_fwd<<<aug_grid(bc * a.Hu * a.Wu), 256, 0, s>>>(images, U, a);
-  mgr::aug_sample<false><<<aug_grid((long long)B * a.Hs * a.Ws), 256, 0, s>>>(theta, U, S, a);
-  mgr::aug_down_fwd<<<aug_grid(bc * H * W), 256, 0, s>>>(S, out, a);
+  float* T = S + bc * a.Hs * a.Ws + bc * a.Hp * a.Wp;
+  using namespace mgr;
+  // reflect pad + x2 upsample: along x ([H, W] -> [H, Wu]), then along y (-> [Hu, Wu])
+  aug_fir_1d<kUp, true><<<aug_grid(bc * H * a.Wu), 256, 0, s>>>(images, T, bc, W, a.Wu, H, mx0);
+  aug_fir_1d<kUp, false><<<aug_grid(bc * a.Hu * a.Wu), 256, 0, s>>>(T, U, bc, H, a.Hu, a.Wu, my0);
+  aug_sample<false><<<aug_grid((long long)B * a.Hs * a.Ws), 256, 0, s>>>(theta, U, S, a);
+  // low-pass + decimate: along x ([Hs, Ws] -> [Hs, W]), then along y (-> [H, W])
+  aug_fir_1d<kDown, true><<<aug_grid(bc * a.Hs * W), 256, 0, s>>>(S, T, bc, a.Ws, W, a.Hs, 0);
+  aug_fir_1d<kDown, false><<<aug_grid(bc * H * W), 256, 0, s>>>(T, out, bc, a.Hs, H, W, 0);
   MGR_CUDA(cudaGetLastError());
-  mgr::count_launch(3);
+  mgr::count_launch(5);
   return MGR_OK;
 }
 
@@ -372,13 +385,19 @@ int mgr_augment_geom_backward(const float* grad_out, const float* theta, float* 
   float* gU = (float*)workspace;
   float* gS = gU + bc * a.Hu * a.Wu;
   float* gxp = gS + bc * a.Hs * a.Ws;
-  mgr::aug_down_bwd<<<aug_grid(bc * a.Hs * a.Ws), 256, 0, s>>>(grad_out, gS, a);
+  float* T = gxp + bc * a.Hp * a.Wp;
+  using namespace mgr;
+  // adjoint of the decimation: along y ([H, W] -> [Hs, W]), then along x (-> [Hs, Ws])
+  aug_fir_1d<kDownAdj, false><<<aug_grid(bc * a.Hs * W), 256, 0, s>>>(grad_out, T, bc, H, a.Hs, W, 0);
+  aug_fir_1d<kDownAdj, true><<<aug_grid(bc * a.Hs * a.Ws), 256, 0, s>>>(T, gS, bc, W, a.Ws, a.Hs, 0);
   MGR_CUDA(cudaMemsetAsync(gU, 0, sizeof(float) * bc * a.Hu * a.Wu, s));
-  mgr::aug_sample<true><<<aug_grid((long long)B * a.Hs * a.Ws), 256, 0, s>>>(theta, gS, gU, a);
-  mgr::aug_up_bwd_padded<<<aug_grid(bc * a.Hp * a.Wp), 256, 0, s>>>(gU, gxp, a);
-  mgr::aug_fold_reflect<<<aug_grid(bc * H * W), 256, 0, s>>>(gxp, grad_images, a);
+  aug_sample<true><<<aug_grid((long long)B * a.Hs * a.Ws), 256, 0, s>>>(theta, gS, gU, a);
+  // adjoint of the upsample w.r.t. the padded image: along x ([Hu, Wu] -> [Hu, Wp]), then along y (-> [Hp, Wp]); fold
+  aug_fir_1d<kUpAdj, true><<<aug_grid(bc * a.Hu * a.Wp), 256, 0, s>>>(gU, T, bc, a.Wu, a.Wp, a.Hu, 0);
+  aug_fir_1d<kUpAdj, false><<<aug_grid(bc * a.Hp * a.Wp), 256, 0, s>>>(T, gxp, bc, a.Hu, a.Hp, a.Wp, 0);
+  aug_fold_reflect<<<aug_grid(bc * H * W), 256, 0, s>>>(gxp, grad_images, a);
   MGR_CUDA(cudaGetLastError());
-  mgr::count_launch(4);
+  mgr::count_launch(6);
   return MGR_OK;
 }
 
