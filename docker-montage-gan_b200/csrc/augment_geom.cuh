@@ -25,6 +25,18 @@ struct AugGeom {
 
 __device__ __forceinline__ int reflect_index(int p, int n) { return p < 0 ? -p : (p >= n ? 2 * (n - 1) - p : p); }
 
+// k -> (plane, row, col) of a [planes][rows][cols] array; 32-bit divisions whenever the index fits (64-bit ones cost
+// more than the 12-tap filters these kernels run)
+__device__ __forceinline__ void split3(long long k, int cols, int rows, int& c, int& r, long long& pl) {
+  if (k < (1LL << 31)) {
+    const unsigned kk = (unsigned)k, q = kk / (unsigned)cols, q2 = q / (unsigned)rows;
+    c = (int)(kk - q * (unsigned)cols); r = (int)(q - q2 * (unsigned)rows); pl = q2;
+  } else {
+    const long long q = k / cols;
+    c = (int)(k - q * cols); pl = q / rows; r = (int)(q - pl * rows);
+  }
+}
+
 // Every FIR stage is separable (upfirdn2d.py:211-216 runs two 1-D convolutions as well): one kernel per axis, a thread
 // per output element, the intermediate in the workspace.  n_out / n_in are the lengths along the filtered axis; the
 // other axis has `other` elements; kAlongX selects which of the two innermost axes is filtered.
@@ -42,8 +54,9 @@ aug_fir_1d(const float* __restrict__ src, float* __restrict__ dst, long long pla
   const int cols_in = kAlongX ? n_in : other, rows_in = kAlongX ? other : n_in;
   const long long total = planes * rows_out * cols_out;
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(k % cols_out), r = (int)((k / cols_out) % rows_out);
-    const long long pl = k / ((long long)cols_out * rows_out);
+    int c, r;
+    long long pl;
+    split3(k, cols_out, rows_out, c, r, pl);
     const int o = kAlongX ? c : r;                             // position along the filtered axis
     const float* p = src + pl * rows_in * cols_in + (kAlongX ? (long long)r * cols_in : c);
     const int step = kAlongX ? 1 : cols_in;
@@ -87,8 +100,10 @@ static __global__ void __launch_bounds__(256)
 aug_sample(const float* __restrict__ theta, const float* __restrict__ src, float* __restrict__ dst, AugGeom a) {
   const long long total = (long long)a.B * a.Hs * a.Ws;
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
-    const int Xs = (int)(k % a.Ws), Ys = (int)((k / a.Ws) % a.Hs);
-    const int b = (int)(k / ((long long)a.Ws * a.Hs));
+    int Xs, Ys;
+    long long bl;
+    split3(k, a.Ws, a.Hs, Xs, Ys, bl);
+    const int b = (int)bl;
     float ix, iy;
     aug_source_coords(theta + b * 6, a, Xs, Ys, ix, iy);
     const float fx0 = floorf(ix), fy0 = floorf(iy);
@@ -131,8 +146,9 @@ static __global__ void __launch_bounds__(256)
 aug_fold_reflect(const float* __restrict__ gxp, float* __restrict__ gimg, AugGeom a) {
   const long long total = (long long)a.B * a.C * a.H * a.W;
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
-    const int x = (int)(k % a.W), y = (int)((k / a.W) % a.H);
-    const long long bc = k / ((long long)a.W * a.H);
+    int x, y;
+    long long bc;
+    split3(k, a.W, a.H, x, y, bc);
     int sx[3], sy[3];
     const int nx = reflect_sources(x, a.W, a.mx0, a.mx1, sx), ny = reflect_sources(y, a.H, a.my0, a.my1, sy);
     const float* p = gxp + bc * a.Hp * a.Wp;
