@@ -115,3 +115,17 @@ def test_new_entry_points_validate_before_touching_memory():
     assert need == 2 * 3 * (128 + 4 + 4) + 32 + 2 * 4                                                 # gather path bookkeeping
     assert lib.mgr_warp_backward_workspace_bytes(2, 3, 8, 8, _lib.MGR_BF16, 1) == 2 * 3 * 4 * 64 * 4  # fp32 scatter accumulator dominates
     assert lib.mgr_warp_backward(0x1000, None, 0x3000, 0x2000, 0x4000, 0x5000, None, 0, 2, 3, 8, 8, 0, 0, 3, None) == 3
+
+
+def test_augment_geom_entry_points_validate():
+    lib = _lib.load()
+    B, C, H, W, m = 2, 4, 16, 16, (3, 2, 1, 0)
+    Hp, Wp = H + m[1] + m[3], W + m[0] + m[2]
+    per_plane = (2 * Hp) * (2 * Wp) + (2 * (H + 6)) * (2 * (W + 6)) + Hp * Wp + max(H * 2 * Wp, 2 * (H + 6) * W, 2 * Hp * Wp)
+    assert lib.mgr_augment_geom_workspace_bytes(B, C, H, W, *m) == 4 * B * C * per_plane
+    assert lib.mgr_augment_geom_workspace_bytes(B, C, H, W, 16, 0, 0, 0) == 0                       # margin > size - 1
+    assert lib.mgr_augment_geom_forward(0x1000, 0x2000, 0x3000, None, 0, B, C, H, W, 16, 0, 0, 0, None) == 1
+    assert b"margins" in lib.mgr_last_error()
+    assert lib.mgr_augment_geom_forward(0x1000, 0x2000, 0x3000, None, 0, B, C, H, W, *m, None) == 3  # workspace too small
+    assert lib.mgr_augment_geom_forward(None, 0x2000, 0x3000, None, 0, B, C, H, W, *m, None) == 1
+    assert lib.mgr_augment_geom_backward(0x1000, 0x2000, 0x3000, None, 0, 0, C, H, W, *m, None) == 0  # empty batch
