@@ -361,7 +361,7 @@ int mgr_augment_geom_forward(const float* images, const float* theta, float* out
   using namespace mgr;
   // reflect pad + x2 upsample: along x ([H, W] -> [H, Wu]), then along y (-> [Hu, Wu])
   aug_fir_1d<kUp, true><<<aug_grid(bc * H * a.Wu), 256, 0, s>>>(images, T, bc, W, a.Wu, H, mx0);
-  aug_fir_1d<kUp, false><<<aug_grid(bc * a.Hu * a.Wu), 256, 0, s>>>(T, U, bc, H, a.Hu, a.Wu, my0);
+  aug_up_y_blocked<<<aug_grid(bc * ((a.Hu + kUpRows - 1) / kUpRows) * a.Wu), 256, 0, s>>>(T, U, bc, H, a.Hu, a.Wu, my0);
   aug_sample<false><<<aug_grid((long long)B * a.Hs * a.Ws), 256, 0, s>>>(theta, U, S, a);
   // low-pass + decimate: along x ([Hs, Ws] -> [Hs, W]), then along y (-> [H, W])
   aug_fir_1d<kDown, true><<<aug_grid(bc * a.Hs * W), 256, 0, s>>>(S, T, bc, a.Ws, W, a.Hs, 0);
