@@ -124,6 +124,48 @@ aug_up_y_blocked(const float* __restrict__ src, float* __restrict__ dst, long lo
   }
 }
 
+// The two adjoint passes along y, blocked the same way.
+//   kDownAdj: outputs Y0 .. Y0 + 7 (Y0 even) read input rows (Y0 - 12) / 2 .. (Y0 + 6) / 2     -> 10 rows for 8 outputs
+//   kUpAdj:   outputs j0 .. j0 + 3 read input rows 2 j0 - 5 .. 2 j0 + 12                        -> 18 rows for 4 outputs
+template <int kOp>
+static __global__ void __launch_bounds__(256)
+aug_adj_y_blocked(const float* __restrict__ src, float* __restrict__ dst, long long planes, int n_in, int n_out, int cols) {
+  constexpr int kRows = kOp == kDownAdj ? 8 : 4;
+  constexpr int kIn = kOp == kDownAdj ? 10 : 18;
+  const int row_blocks = (n_out + kRows - 1) / kRows;
+  const long long total = planes * row_blocks * cols;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += (long long)gridDim.x * blockDim.x) {
+    int c, rb;
+    long long pl;
+    split3(k, cols, row_blocks, c, rb, pl);
+    const int o0 = rb * kRows;
+    const float* p = src + pl * n_in * cols + c;
+    const int i0 = kOp == kDownAdj ? (o0 - 12) / 2 : 2 * o0 - 5;
+    float v[kIn];
+#pragma unroll
+    for (int q = 0; q < kIn; ++q) {
+      const int i = i0 + q;
+      v[q] = (i >= 0 && i < n_in) ? p[(long long)i * cols] : 0.f;
+    }
+    float* o = dst + pl * n_out * cols + (long long)o0 * cols + c;
+#pragma unroll
+    for (int d = 0; d < kRows; ++d) {
+      if (o0 + d >= n_out) break;
+      float acc = 0.f;
+      if (kOp == kDownAdj) {
+#pragma unroll
+        for (int t = (d + 1) & 1; t < kFir; t += 2)            // x2 = o0 + d - 1 - t even; input row x2 / 2 = i0 + (d + 11 - t) / 2
+          acc = fmaf(c_sym6[t], v[(d + 11 - t) >> 1], acc);
+      } else {
+#pragma unroll
+        for (int t = 0; t < kFir; ++t)                         // input row 2 (o0 + d) + 6 - t = i0 + 2 d + 11 - t
+          acc = fmaf(2.f * c_sym6[kFir - 1 - t], v[2 * d + 11 - t], acc);
+      }
+      o[(long long)d * cols] = acc;
+    }
+  }
+}
+
 // pixel (Xs, Ys) of the resampling grid -> source coordinates in U (affine_grid + grid_sample unnormalisation)
 __device__ __forceinline__ void aug_source_coords(const float* __restrict__ th, const AugGeom& a, int Xs, int Ys, float& ix, float& iy) {
   const float xn = (2.f * Xs + 1.f) / a.Ws - 1.f, yn = (2.f * Ys + 1.f) / a.Hs - 1.f;

@@ -388,13 +388,13 @@ int mgr_augment_geom_backward(const float* grad_out, const float* theta, float* 
   float* T = gxp + bc * a.Hp * a.Wp;
   using namespace mgr;
   // adjoint of the decimation: along y ([H, W] -> [Hs, W]), then along x (-> [Hs, Ws])
-  aug_fir_1d<kDownAdj, false><<<aug_grid(bc * a.Hs * W), 256, 0, s>>>(grad_out, T, bc, H, a.Hs, W, 0);
+  aug_adj_y_blocked<kDownAdj><<<aug_grid(bc * ((a.Hs + 7) / 8) * W), 256, 0, s>>>(grad_out, T, bc, H, a.Hs, W);
   aug_fir_1d<kDownAdj, true><<<aug_grid(bc * a.Hs * a.Ws), 256, 0, s>>>(T, gS, bc, W, a.Ws, a.Hs, 0);
   MGR_CUDA(cudaMemsetAsync(gU, 0, sizeof(float) * bc * a.Hu * a.Wu, s));
   aug_sample<true><<<aug_grid((long long)B * a.Hs * a.Ws), 256, 0, s>>>(theta, gS, gU, a);
   // adjoint of the upsample w.r.t. the padded image: along x ([Hu, Wu] -> [Hu, Wp]), then along y (-> [Hp, Wp]); fold
   aug_fir_1d<kUpAdj, true><<<aug_grid(bc * a.Hu * a.Wp), 256, 0, s>>>(gU, T, bc, a.Wu, a.Wp, a.Hu, 0);
-  aug_fir_1d<kUpAdj, false><<<aug_grid(bc * a.Hp * a.Wp), 256, 0, s>>>(T, gxp, bc, a.Hu, a.Hp, a.Wp, 0);
+  aug_adj_y_blocked<kUpAdj><<<aug_grid(bc * ((a.Hp + 3) / 4) * a.Wp), 256, 0, s>>>(T, gxp, bc, a.Hu, a.Hp, a.Wp);
   aug_fold_reflect<<<aug_grid(bc * H * W), 256, 0, s>>>(gxp, grad_images, a);
   MGR_CUDA(cudaGetLastError());
   mgr::count_launch(6);
