@@ -62,15 +62,20 @@ aug_fir_1d(const float* __restrict__ src, float* __restrict__ dst, long long pla
     const int step = kAlongX ? 1 : cols_in;
     float acc = 0.f;
     if (kOp == kUp) {
-      for (int t = o & 1; t < kFir; t += 2) {
+      // every tap is evaluated (out-of-range ones with weight 0 on a clamped address): no data-dependent branches, so
+      // the loads of one output issue back to back instead of one dependent round trip per tap
+#pragma unroll
+      for (int q = 0; q < kFir / 2; ++q) {
+        const int t = (o & 1) + 2 * q;
         const int u = o + t - 6;                               // position in the zero-inserted padded signal (even here)
-        if (u < 0 || u >= n_out) continue;
-        acc = fmaf(2.f * c_sym6[kFir - 1 - t], p[(long long)reflect_index((u >> 1) - m0, n_in) * step], acc);
+        const bool ok = u >= 0 && u < n_out;
+        const int idx = min(max(reflect_index((max(u, 0) >> 1) - m0, n_in), 0), n_in - 1);
+        acc = fmaf(ok ? 2.f * c_sym6[kFir - 1 - t] : 0.f, p[(long long)idx * step], acc);
       }
     } else if (kOp == kDown) {
 #pragma unroll
       for (int t = 0; t < kFir; ++t) acc = fmaf(c_sym6[t], p[(long long)(2 * o + t + 1) * step], acc);
-    } else if (kOp == kDownAdj) {
+    } else if (kOp == kDownAdj) {                              // (the branch-free form was measured slower for the adjoints)
       for (int t = (o - 1) & 1; t < kFir; t += 2) {
         const int x2 = o - 1 - t;
         if (x2 < 0 || (x2 >> 1) >= n_in) continue;
