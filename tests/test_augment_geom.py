@@ -53,6 +53,19 @@ def test_oracle_filters_known_answers():
     assert float((y - xs)[:, :, 4:-4, 4:-4].abs().max()) < 2e-2
 
 
+def test_host_side_margins_and_matrices_match_reference(golden):
+    """The product's host logic (montage_gan_b200.augment: padding margins, the matrices for the sampler) is plain CPU
+    arithmetic: it must reproduce what the reference pipe asked of F.pad and affine_grid."""
+    from montage_gan_b200 import augment as A
+    for n in [str(v) for v in golden["names"]]:
+        Gi = torch.from_numpy(golden[f"{n}/G_inv"])
+        H, W = golden[f"{n}/images"].shape[2:]
+        m = A.padding_margins(Gi, H, W)
+        assert m == tuple(int(v) for v in golden[f"{n}/margins"]), n
+        th = A.sampling_theta(Gi, H, W, *m)
+        assert float((th - torch.from_numpy(golden[f"{n}/theta"])).abs().max()) < 1e-6, n
+
+
 # ------------------------------------------------------------------------------------------------ GPU
 @pytest.mark.gpu
 def test_cuda_matches_reference_golden(golden):
