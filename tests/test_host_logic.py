@@ -46,3 +46,37 @@ def test_synth_is_deterministic_and_in_range():
         assert t.shape == (2, 5, 2, 3) and torch.equal(t, synth.make_theta(2, 5, fam, seed=3))
     t = synth.make_theta(2, 5, "T", seed=3, cover_back=False)
     assert torch.equal(t[..., :2], torch.eye(2).expand(2, 5, 2, 2)) and t[..., 2].abs().max() <= 1
+
+
+def test_every_public_entry_refuses_cpu_tensors():
+    """No CPU fallback anywhere in the product: each public function raises MontageRenderError for CPU tensors instead of
+    computing something (the oracle under oracle/ is test infrastructure and is never reached from the package)."""
+    from montage_gan_b200 import augment as A, render as mr
+    x = torch.zeros(1, 3, 4, 16, 16)
+    th = torch.eye(2, 3).expand(1, 3, 2, 3).contiguous()
+    layers = [torch.zeros(1, 4, 16, 16), torch.zeros(1, 4, 8, 8)]
+    calls = [
+        lambda: mr.render(x, th),
+        lambda: mr.render(x, None),
+        lambda: mr.warp(x, th),
+        lambda: mr.alpha_composite_pytorch((x + 1) / 2),
+        lambda: mr.alpha_composite((x + 1) / 2),
+        lambda: mr.render_ragged(layers, th[:, :2], canvas=(16, 16)),
+        lambda: mr.convert_translate_to_2x3(torch.zeros(1, 3, 2)),
+        lambda: mr.random_position((x + 1) / 2),
+        lambda: A.geometric_warp(torch.zeros(1, 4, 16, 16), torch.eye(3)),
+    ]
+    for k, call in enumerate(calls):
+        with pytest.raises(_lib.MontageRenderError):
+            call()
+
+
+def test_package_never_imports_the_oracle():
+    """The product path must not route through oracle/: no module of the package mentions it."""
+    import os
+    pkg = os.path.dirname(montage_gan_b200.__file__)
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(root, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f
