@@ -55,46 +55,60 @@ def _p(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+def _launch(entry: str, x: torch.Tensor, theta: torch.Tensor, margins) -> torch.Tensor:
+    """One call of ``mgr_augment_geom_forward`` / ``_backward`` on a detached, contiguous fp32 ``x [B,C,H,W]``."""
+    lib = _lib.load()
+    B, C, H, W = x.shape
+    y = torch.empty_like(x)
+    nbytes = lib.mgr_augment_geom_workspace_bytes(B, C, H, W, *margins)
+    ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = getattr(lib, entry)(_p(x), _p(theta), _p(y), _p(ws), nbytes, B, C, H, W, *margins,
+                                 ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
+    _lib.check(rc, entry)
+    _lib.launch_count += 1
+    return y
+
+
+# The block is LINEAR in the images (pad, FIR, bilinear resampling, FIR): its backward is the adjoint operator applied
+# to grad_out, and the backward of THAT is the forward operator applied to the incoming cotangent.  The two Functions
+# below call each other, so the block differentiates to any order -- what the reference gets from
+# grid_sample_gradfix (torch_utils/ops/grid_sample_gradfix.py:49-88) and upfirdn2d's own double backward, and what the
+# R1 penalty needs: autograd.grad(real_logits.sum(), real_layer_tmp, create_graph=True) runs through the augment pipe
+# that sits between the renderer and global D (custom/loss_aio.py:252-254, 327-338).
 class _GeometricWarp(torch.autograd.Function):
     @staticmethod
     def forward(ctx, images, theta, margins):
-        lib = _lib.load()
-        B, C, H, W = images.shape
-        x = images.detach().contiguous()
-        out = torch.empty_like(x)
-        nbytes = lib.mgr_augment_geom_workspace_bytes(B, C, H, W, *margins)
-        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=x.device)
-        with torch.cuda.device(x.device):
-            rc = lib.mgr_augment_geom_forward(_p(x), _p(theta), _p(out), _p(ws), nbytes, B, C, H, W, *margins,
-                                              ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
-        _lib.check(rc, "mgr_augment_geom_forward")
-        _lib.launch_count += 1
         ctx.margins = margins
         ctx.save_for_backward(theta)
-        return out
+        return _launch("mgr_augment_geom_forward", images.detach().contiguous(), theta, margins)
 
     @staticmethod
     def backward(ctx, grad_out):
         if not ctx.needs_input_grad[0]:
             return None, None, None
         (theta,) = ctx.saved_tensors
-        lib = _lib.load()
-        go = grad_out.detach().to(torch.float32).contiguous()
-        B, C, H, W = go.shape
-        gi = torch.empty_like(go)
-        nbytes = lib.mgr_augment_geom_workspace_bytes(B, C, H, W, *ctx.margins)
-        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=go.device)
-        with torch.cuda.device(go.device):
-            rc = lib.mgr_augment_geom_backward(_p(go), _p(theta), _p(gi), _p(ws), nbytes, B, C, H, W, *ctx.margins,
-                                               ctypes.c_void_p(torch.cuda.current_stream(go.device).cuda_stream))
-        _lib.check(rc, "mgr_augment_geom_backward")
-        _lib.launch_count += 1
-        return gi, None, None
+        return _GeometricWarpAdjoint.apply(grad_out, theta, ctx.margins), None, None
+
+
+class _GeometricWarpAdjoint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, grad_out, theta, margins):
+        ctx.margins = margins
+        ctx.save_for_backward(theta)
+        return _launch("mgr_augment_geom_backward", grad_out.detach().to(torch.float32).contiguous(), theta, margins)
+
+    @staticmethod
+    def backward(ctx, grad_grad):
+        if not ctx.needs_input_grad[0]:
+            return None, None, None
+        (theta,) = ctx.saved_tensors
+        return _GeometricWarp.apply(grad_grad.to(torch.float32), theta, ctx.margins), None, None
 
 
 def geometric_warp(images: torch.Tensor, G_inv: torch.Tensor) -> torch.Tensor:
     """``images [B,C,H,W]`` fp32 on the GPU, ``G_inv [B,3,3]`` (or ``[3,3]``): the inverse pixel-space transform the pipe
-    has accumulated.  Returns the transformed images; differentiable w.r.t. ``images`` (G_inv is random, not learned).
+    has accumulated.  Returns the transformed images; differentiable w.r.t. ``images`` to any order (G_inv is random, not learned).
     A G_inv that is the identity object short-circuits in the reference (augment.py:309); pass it anyway and the block
     runs as a mild low-pass, or skip the call as the reference does."""
     if images.dim() != 4 or images.dtype != torch.float32:

@@ -11,7 +11,10 @@ The FIR arithmetic lives in ``torch_utils/ops/upfirdn2d.py:168-222`` (``_upfirdn
 two 1-D convolutions, decimation); restated below with plain convolutions.  Pinned by
 ``tests/golden/augment_geom_golden.npz`` (``oracle/make_golden_augment.py``: the reference pipe itself, run on CPU).
 
-Status: oracle + golden vectors only -- the CUDA kernels for this row are the next round's work.
+``geometric_warp(..., double_backward=True)`` swaps ATen's ``grid_sample`` (whose backward has no derivative -- the
+reason the reference carries ``torch_utils/ops/grid_sample_gradfix.py``) for ``bilinear_sample`` below, the same
+arithmetic written with index gathers, so that the R1 pattern (``custom/loss_aio.py:327-338``) can be differentiated
+twice on the CPU.
 """
 from __future__ import annotations
 
@@ -92,8 +95,30 @@ def sampling_theta(G_inv, H, W, mx0, my0, mx1, my1, hz_pad: int = 3):
     return G[:, :2, :], (Hs, Ws)
 
 
-def geometric_warp(images: torch.Tensor, G_inv: torch.Tensor, hz_pad: int = 3) -> torch.Tensor:
-    """The whole block for ``images [B,C,H,W]`` (fp32 / fp64, CPU) and ``G_inv [B,3,3]``; differentiable via autograd."""
+def bilinear_sample(x: torch.Tensor, grid: torch.Tensor) -> torch.Tensor:
+    """``F.grid_sample(x, grid, 'bilinear', 'zeros', align_corners=False)`` with plain indexing (ATen
+    ``GridSampler.h:27-36, 205-207``: unnormalise, four corners, out-of-range corners contribute 0).  Linear in ``x`` and
+    built from ops that autograd differentiates to any order."""
+    B, C, H, W = x.shape
+    ix = ((grid[..., 0] + 1) * W - 1) / 2
+    iy = ((grid[..., 1] + 1) * H - 1) / 2
+    x0, y0 = torch.floor(ix), torch.floor(iy)
+    fx, fy = (ix - x0)[:, None], (iy - y0)[:, None]
+    x0, y0 = x0.long(), y0.long()
+    flat = x.reshape(B, C, H * W)
+
+    def tap(yy, xx):
+        inside = ((xx >= 0) & (xx < W) & (yy >= 0) & (yy < H))[:, None].to(x.dtype)
+        idx = (yy.clamp(0, H - 1) * W + xx.clamp(0, W - 1)).reshape(B, 1, -1).expand(B, C, -1)
+        return torch.gather(flat, 2, idx).reshape(B, C, *grid.shape[1:3]) * inside
+
+    return (tap(y0, x0) * (1 - fx) * (1 - fy) + tap(y0, x0 + 1) * fx * (1 - fy) +
+            tap(y0 + 1, x0) * (1 - fx) * fy + tap(y0 + 1, x0 + 1) * fx * fy)
+
+
+def geometric_warp(images: torch.Tensor, G_inv: torch.Tensor, hz_pad: int = 3, double_backward: bool = False) -> torch.Tensor:
+    """The whole block for ``images [B,C,H,W]`` (fp32 / fp64, CPU) and ``G_inv [B,3,3]``; differentiable via autograd
+    (twice with ``double_backward=True``)."""
     B, C, H, W = images.shape
     f = lowpass_filter()
     mx0, my0, mx1, my1 = margins(G_inv.float(), H, W, hz_pad)
@@ -101,7 +126,10 @@ def geometric_warp(images: torch.Tensor, G_inv: torch.Tensor, hz_pad: int = 3) -
     x = upsample2x(x, f)
     theta, (Hs, Ws) = sampling_theta(G_inv.float(), H, W, mx0, my0, mx1, my1, hz_pad)
     grid = F.affine_grid(theta.to(images.dtype), [B, C, Hs, Ws], align_corners=False)
-    x = F.grid_sample(x, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+    if double_backward:
+        x = bilinear_sample(x, grid)
+    else:
+        x = F.grid_sample(x, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
     return downsample2x(x, f, -hz_pad * 2)
 
 

@@ -53,6 +53,23 @@ def test_oracle_filters_known_answers():
     assert float((y - xs)[:, :, 4:-4, 4:-4].abs().max()) < 2e-2
 
 
+def test_oracle_index_sampler_equals_grid_sample():
+    """oracle.bilinear_sample (the twice-differentiable stand-in) against ATen's grid_sample, value and first gradient."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 3, 17, 23, generator=g, dtype=torch.float64).requires_grad_(True)
+    theta = torch.eye(2, 3, dtype=torch.float64).repeat(2, 1, 1) + 0.3 * torch.randn(2, 2, 3, generator=g, dtype=torch.float64)
+    grid = torch.nn.functional.affine_grid(theta, [2, 3, 20, 26], align_corners=False)
+    a = AG.bilinear_sample(x, grid)
+    b = torch.nn.functional.grid_sample(x, grid, mode="bilinear", padding_mode="zeros", align_corners=False)
+    assert float((a - b).abs().max()) < 1e-12
+    go = torch.randn(a.shape, generator=g, dtype=torch.float64)
+    (ga,), (gb,) = torch.autograd.grad(a, x, go), torch.autograd.grad(b, x, go)
+    assert float((ga - gb).abs().max()) < 1e-12
+    xs = torch.rand(1, 2, 24, 24, generator=g)
+    Gi = torch.tensor([[[0.9, 0.2, 1.5], [-0.2, 1.1, -2.0], [0.0, 0.0, 1.0]]])
+    assert float((AG.geometric_warp(xs, Gi, double_backward=True) - AG.geometric_warp(xs, Gi)).abs().max()) < 1e-6
+
+
 def test_host_side_margins_and_matrices_match_reference(golden):
     """The product's host logic (montage_gan_b200.augment: padding margins, the matrices for the sampler) is plain CPU
     arithmetic: it must reproduce what the reference pipe asked of F.pad and affine_grid."""
@@ -101,6 +118,66 @@ def test_cuda_forward_and_gradient_match_oracle(shape):
     (gd,) = torch.autograd.grad(out, xd, go.cuda())
     assert float((out.detach().cpu() - ref.detach()).abs().max()) < 5e-5
     assert float((gd.cpu() - gref).abs().max() / gref.abs().max()) < 1e-4
+
+
+@pytest.mark.gpu
+def test_cuda_double_backward_is_the_forward_operator():
+    """The block is linear: d/d(grad_out) of <A^T grad_out, v> is A v.  The backward used to detach grad_out, so under
+    create_graph=True the result silently had no graph (round-1 ADVICE, high)."""
+    from montage_gan_b200 import augment as A
+    g = torch.Generator().manual_seed(3)
+    B, C, H, W = 2, 4, 40, 48
+    Gi = torch.eye(3).repeat(B, 1, 1)
+    Gi[:, 0, 1], Gi[:, 1, 0], Gi[:, 0, 2] = 0.2, -0.15, 3.5
+    x = (torch.rand(B, C, H, W, generator=g) * 2 - 1).cuda().requires_grad_(True)
+    go = torch.randn(B, C, H, W, generator=g).cuda().requires_grad_(True)
+    v = torch.randn(B, C, H, W, generator=g).cuda()
+    out = A.geometric_warp(x, Gi)
+    (gi,) = torch.autograd.grad(out, x, go, create_graph=True)
+    assert gi.requires_grad                                             # the graph through grad_out survives
+    (ggo,) = torch.autograd.grad(gi, go, v, create_graph=True)
+    assert float((ggo - A.geometric_warp(v, Gi)).abs().max()) < 1e-5
+    (third,) = torch.autograd.grad(ggo, v if v.requires_grad else go, torch.ones_like(ggo), allow_unused=True)
+    assert third is None or torch.isfinite(third).all()
+
+
+@pytest.mark.gpu
+def test_r1_penalty_through_the_block_matches_oracle():
+    """custom/loss_aio.py:327-338 with the augment pipe of :252-254 in between: r1_grads = autograd.grad(logits.sum(),
+    images, create_graph=True); the penalty's gradient w.r.t. D's weights flows through the block's double backward
+    (reference: grid_sample_gradfix.py:49-88).  D here is a two-layer conv net with a smooth non-linearity."""
+    from montage_gan_b200 import augment as A
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(11)
+    B, C, H, W = 2, 4, 48, 40
+    x = torch.rand(B, C, H, W, generator=g) * 2 - 1
+    ang = torch.tensor([0.3, -0.5])
+    Gi = torch.eye(3).repeat(B, 1, 1)
+    Gi[:, 0, 0], Gi[:, 0, 1], Gi[:, 1, 0], Gi[:, 1, 1] = torch.cos(ang), -torch.sin(ang), torch.sin(ang), torch.cos(ang)
+    Gi[:, 0, 2], Gi[:, 1, 2] = torch.tensor([2.25, -4.5]), torch.tensor([-1.75, 3.0])
+    w1 = torch.randn(8, C, 3, 3, generator=g) * 0.3
+    w2 = torch.randn(1, 8, 3, 3, generator=g) * 0.3
+
+    def r1(geom, x_, w1_, w2_):
+        x_ = x_.requires_grad_(True)
+        w1_, w2_ = w1_.requires_grad_(True), w2_.requires_grad_(True)
+        logits = F.conv2d(torch.tanh(F.conv2d(geom(x_, Gi), w1_, padding=1)), w2_, padding=1).mean([1, 2, 3])
+        (r1_grads,) = torch.autograd.grad(logits.sum(), x_, create_graph=True, only_inputs=True)
+        penalty = r1_grads.square().sum([1, 2, 3]).mean()
+        gw = torch.autograd.grad(penalty, [w1_, w2_])
+        return penalty.detach().cpu().double(), [t.detach().cpu().double() for t in gw]
+
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        pen, gw = r1(A.geometric_warp, x.cuda(), w1.cuda(), w2.cuda())
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    pen_ref, gw_ref = r1(lambda im, G: AG.geometric_warp(im, G, double_backward=True), x.double(), w1.double(), w2.double())
+    assert float(gw_ref[0].abs().max()) > 0 and float(gw_ref[1].abs().max()) > 0
+    assert abs(float(pen - pen_ref)) <= 1e-4 * abs(float(pen_ref))
+    for a, r in zip(gw, gw_ref):
+        assert float((a - r).abs().max() / r.abs().max()) < 1e-3
 
 
 @pytest.mark.gpu
