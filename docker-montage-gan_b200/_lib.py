@@ -85,6 +85,13 @@ def load(build_if_missing: bool = True):
             except Exception as exc:  # noqa: BLE001
                 if not os.path.isfile(LIB_PATH):
                     raise MontageRenderError(f"libmontage_render.so is missing and could not be built: {exc}") from exc
+                # a library exists but its sources changed and the rebuild failed: loading it would silently run old
+                # kernels under new host code.  Opt in explicitly (MGR_ALLOW_STALE_LIB=1) to do that.
+                if os.environ.get("MGR_ALLOW_STALE_LIB") != "1":
+                    raise MontageRenderError("libmontage_render.so is stale (source hash mismatch) and the rebuild failed: "
+                                             f"{exc}; set MGR_ALLOW_STALE_LIB=1 to load it anyway") from exc
+                import warnings
+                warnings.warn(f"loading a STALE libmontage_render.so (rebuild failed: {exc})", RuntimeWarning)
         if not os.path.isfile(LIB_PATH):
             raise MontageRenderError(f"{LIB_PATH} not found; run `python __graft_entry__.py build`")
         lib = ctypes.CDLL(LIB_PATH)

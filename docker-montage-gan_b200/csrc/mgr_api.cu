@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstring>
 #include <atomic>
+#include <mutex>
 
 #include "montage_render.h"
 #include "mgr_common.cuh"
@@ -405,6 +406,36 @@ int mgr_augment_geom_backward(const float* grad_out, const float* theta, float* 
 namespace {
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 struct HostSlot { char *x, *theta, *go, *out, *sav, *gx, *gt, *ws; };
+// Two copy streams and the events that order them, created once per device and kept for the life of the process
+// (creating and destroying them per call cost ~60 us of host time and leaked on error paths).
+struct HostPipe {
+  std::mutex mu;
+  bool ready = false;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  cudaEvent_t start = nullptr, done_in = nullptr, done_out = nullptr, h2d[2] = {}, comp[2] = {}, freed[2] = {};
+  int init() {                                      // caller holds mu
+    if (ready) return MGR_OK;
+    cudaEvent_t* ev[] = {&start, &done_in, &done_out, &h2d[0], &h2d[1], &comp[0], &comp[1], &freed[0], &freed[1]};
+    cudaError_t e = cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking);
+    for (cudaEvent_t* p : ev)
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(p, cudaEventDisableTiming);
+    if (e != cudaSuccess) {                         // all or nothing
+      for (cudaEvent_t* p : ev) { if (*p) cudaEventDestroy(*p); *p = nullptr; }
+      if (s_in) cudaStreamDestroy(s_in);
+      if (s_out) cudaStreamDestroy(s_out);
+      s_in = s_out = nullptr;
+      return mgr::cuda_fail(e, "host pipeline: stream / event creation");
+    }
+    ready = true;
+    return MGR_OK;
+  }
+};
+constexpr int kMaxDevices = 64;
+HostPipe* host_pipe(int device) {
+  static HostPipe pipes[kMaxDevices];
+  return (device >= 0 && device < kMaxDevices) ? &pipes[device] : nullptr;
+}
 size_t host_slot_bytes(int cb, int L, int H, int W, int dtype, HostSlot* s, char* base) {
   const size_t es = dtype == MGR_F32 ? 4 : 2;
   const size_t nx = (size_t)cb * L * 4 * H * W * es, no = (size_t)cb * 4 * H * W * es, nt = (size_t)cb * L * 6 * 4;
@@ -440,26 +471,36 @@ int mgr_render_fwd_bwd_host(const void* h_x, const float* h_theta, const void* h
   host_slot_bytes(chunk_B, L, H, W, dtype, &slot[1], (char*)d_workspace + per);
   const size_t es = dtype == MGR_F32 ? 4 : 2;
   const size_t sx = (size_t)L * 4 * H * W * es, so = (size_t)4 * H * W * es, st_ = (size_t)L * 6 * 4;   // bytes per sample
-  cudaStream_t user = (cudaStream_t)stream, s_in, s_out;
-  MGR_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
-  MGR_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
-  cudaEvent_t start, h2d[2], comp[2], freed[2];
-  MGR_CUDA(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
-  for (int k = 0; k < 2; ++k) {
-    MGR_CUDA(cudaEventCreateWithFlags(&h2d[k], cudaEventDisableTiming));
-    MGR_CUDA(cudaEventCreateWithFlags(&comp[k], cudaEventDisableTiming));
-    MGR_CUDA(cudaEventCreateWithFlags(&freed[k], cudaEventDisableTiming));
-  }
+  cudaStream_t user = (cudaStream_t)stream;
+  int device = 0;
+  MGR_CUDA(cudaGetDevice(&device));
+  HostPipe* pipe = host_pipe(device);
+  if (!pipe) return fail(MGR_ERR_UNSUPPORTED, "device ordinal %d out of range for the host pipeline", device);
+  // the pipe's events are re-recorded by every call: one call at a time per device enqueues (the enqueue is host work
+  // of ~100 us; the device side of consecutive calls still overlaps as far as the caller's streams allow)
+  std::lock_guard<std::mutex> lock(pipe->mu);
+  if (int rc = pipe->init()) return rc;
+  cudaStream_t s_in = pipe->s_in, s_out = pipe->s_out;
+  cudaEvent_t* h2d = pipe->h2d; cudaEvent_t* comp = pipe->comp; cudaEvent_t* freed = pipe->freed;
   // the copy streams start after whatever the caller has queued on `user`
-  MGR_CUDA(cudaEventRecord(start, user));
-  MGR_CUDA(cudaStreamWaitEvent(s_in, start, 0));
-  MGR_CUDA(cudaStreamWaitEvent(s_out, start, 0));
-  int rc = MGR_OK;
+  MGR_CUDA(cudaEventRecord(pipe->start, user));
+  MGR_CUDA(cudaStreamWaitEvent(s_in, pipe->start, 0));
+  MGR_CUDA(cudaStreamWaitEvent(s_out, pipe->start, 0));
+  // From here on every exit path -- success, a failed launch, a failed copy -- makes `user` wait for both copy streams,
+  // so the caller's next work on `user` (or the next call's reuse of the device slots) never races copies in flight.
+  struct Join {
+    cudaStream_t user, s_in, s_out;
+    cudaEvent_t e_in, e_out;
+    ~Join() {
+      if (cudaEventRecord(e_in, s_in) == cudaSuccess) cudaStreamWaitEvent(user, e_in, 0);
+      if (cudaEventRecord(e_out, s_out) == cudaSuccess) cudaStreamWaitEvent(user, e_out, 0);
+    }
+  } join{user, s_in, s_out, pipe->done_in, pipe->done_out};
   // The last D2H runs with the H2D engine idle (and the first H2D with the D2H engine idle), so the tail of the
   // batch is cut into progressively smaller chunks: chunk_B, ..., chunk_B/2, chunk_B/4, chunk_B/4.
   const int min_cb = chunk_B >= 4 ? chunk_B / 4 : 1;
   int b0 = 0;
-  for (int c = 0; b0 < B && rc == MGR_OK; ++c) {
+  for (int c = 0; b0 < B; ++c) {
     const int k = c & 1, left = B - b0;
     int cb = left < chunk_B ? left : chunk_B;
     if (left <= chunk_B && cb > min_cb) cb = (cb / 2 > min_cb) ? cb / 2 : min_cb;
@@ -473,12 +514,11 @@ int mgr_render_fwd_bwd_host(const void* h_x, const float* h_theta, const void* h
     MGR_CUDA(cudaEventRecord(h2d[k], s_in));
     MGR_CUDA(cudaStreamWaitEvent(user, h2d[k], 0));
     if (c >= 2) MGR_CUDA(cudaStreamWaitEvent(user, freed[k], 0));
-    rc = mgr_render_forward(S.x, nullptr, (const float*)S.theta, S.out, S.sav, cb, L, H, W, dtype, range_mode, user);
-    if (rc == MGR_OK)
-      rc = mgr_render_backward(S.x, nullptr, (const float*)S.theta, S.out, S.go, S.sav, S.gx, (float*)S.gt, S.ws,
-                               mgr_render_backward_workspace_bytes(cb, L, H, W, dtype, 1, 3), cb, L, H, W, dtype,
-                               range_mode, 3, user);
-    if (rc != MGR_OK) break;
+    if (int rc = mgr_render_forward(S.x, nullptr, (const float*)S.theta, S.out, S.sav, cb, L, H, W, dtype, range_mode, user)) return rc;
+    if (int rc = mgr_render_backward(S.x, nullptr, (const float*)S.theta, S.out, S.go, S.sav, S.gx, (float*)S.gt, S.ws,
+                                     mgr_render_backward_workspace_bytes(cb, L, H, W, dtype, 1, 3), cb, L, H, W, dtype,
+                                     range_mode, 3, user))
+      return rc;
     MGR_CUDA(cudaEventRecord(comp[k], user));
     MGR_CUDA(cudaStreamWaitEvent(s_out, comp[k], 0));
     MGR_CUDA(cudaMemcpyAsync((char*)h_out + b0 * so, S.out, cb * so, cudaMemcpyDeviceToHost, s_out));
@@ -487,19 +527,7 @@ int mgr_render_fwd_bwd_host(const void* h_x, const float* h_theta, const void* h
     MGR_CUDA(cudaEventRecord(freed[k], s_out));
     b0 += cb;
   }
-  // `user` completes only when the last results have landed on the host
-  if (rc == MGR_OK) {
-    cudaEvent_t done;
-    MGR_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
-    MGR_CUDA(cudaEventRecord(done, s_out));
-    MGR_CUDA(cudaStreamWaitEvent(user, done, 0));
-    cudaEventDestroy(done);
-  }
-  cudaEventDestroy(start);
-  for (int k = 0; k < 2; ++k) { cudaEventDestroy(h2d[k]); cudaEventDestroy(comp[k]); cudaEventDestroy(freed[k]); }
-  cudaStreamDestroy(s_in);        // destruction is deferred by the runtime until the queued work has drained
-  cudaStreamDestroy(s_out);
-  return rc;
+  return MGR_OK;                  // ~Join: `user` completes only when the last results have landed on the host
 }
 
 }  // extern "C"

@@ -62,11 +62,15 @@ class STNv2b(nn.Module):
         self.fc_loc[2].weight.data.zero_()
         self.fc_loc[2].bias.data.zero_()
 
-    def predict_theta(self, x):
+    def predict_translation(self, x):
+        """The localisation CNN + regression head alone (``networks.py:236-245``): ``[B,L,C,H,W] -> [B,L,2]``.  Plain
+        ``torch.nn`` on whatever device ``x`` lives on."""
         b, l, c, h, w = x.shape
         feat = self.localization(x.reshape(b, l * c, h, w)).reshape(-1, self.len_loc)
-        translation = self.fc_loc(feat).view(b, l, 2)
-        return _r.convert_translate_to_2x3(translation)          # [B,L,2,3]
+        return self.fc_loc(feat).view(b, l, 2)
+
+    def predict_theta(self, x):
+        return _r.convert_translate_to_2x3(self.predict_translation(x))          # [B,L,2,3]
 
     def forward(self, x):
         """[B,L,C,H,W] -> ([B,L,C,H,W] warped (or un-warped if fused), [B,L,2,3] theta)."""

@@ -80,3 +80,24 @@ def test_package_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(root, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_stale_library_is_not_loaded_silently(monkeypatch):
+    """If the sources changed and the rebuild fails, load() raises instead of loading the old .so (round-1 ADVICE);
+    MGR_ALLOW_STALE_LIB=1 opts in, with a warning."""
+    import os
+    from montage_gan_b200 import build as mbuild
+    if not os.path.isfile(_lib.LIB_PATH):
+        pytest.skip("library not built")
+
+    def boom(*a, **k):
+        raise RuntimeError("nvcc exploded")
+
+    monkeypatch.setattr(mbuild, "build", boom)
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.delenv("MGR_ALLOW_STALE_LIB", raising=False)
+    with pytest.raises(_lib.MontageRenderError, match="stale"):
+        _lib.load()
+    monkeypatch.setenv("MGR_ALLOW_STALE_LIB", "1")
+    with pytest.warns(RuntimeWarning, match="STALE"):
+        assert _lib.load() is not None
