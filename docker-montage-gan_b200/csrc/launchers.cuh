@@ -10,8 +10,31 @@
 #include "warp_tiled.cuh"
 #include "pil_composite.cuh"
 #include "composite_only.cuh"
+#include "render_ws.cuh"
+
+#include <mutex>
+#include <map>
+#include <utility>
 
 namespace mgr {
+
+// Opt a kernel in to more than 48 KB of dynamic shared memory when a launch first needs it (and again only if a later
+// launch needs more) instead of on every launch: cudaFuncSetAttribute is a driver call of a few microseconds.
+template <typename Kern>
+int ensure_dynamic_smem(Kern kern, size_t bytes) {
+  if (bytes <= 40 * 1024) return MGR_OK;          // static shared memory counts against the default 48 KB too
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> granted;
+  int dev = 0;
+  MGR_CUDA(cudaGetDevice(&dev));
+  const std::pair<const void*, int> key(reinterpret_cast<const void*>(kern), dev);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = granted.find(key);
+  if (it != granted.end() && it->second >= bytes) return MGR_OK;
+  MGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  granted[key] = bytes;
+  return MGR_OK;
+}
 
 // The tiled kernels stage footprints with 128-bit vector loads (4 fp32 / 8 16-bit texels): every
 // plane row must start on a vector boundary and W must be a multiple of the vector width (a lane's
@@ -75,6 +98,19 @@ const char* ragged_problem(const SrcLayers& src, const DstLayers* dst, const Geo
   return nullptr;
 }
 
+// 16-bit footprints are staged in 8-texel items (128-bit loads) when every row of every layer starts on a 16-byte
+// boundary and the rectangles are multiples of 8 texels (render_ws.cuh: stage_flat); narrow items otherwise
+template <typename T>
+Geometry with_vec8(const SrcLayers& src, const Geometry& g) {
+  Geometry r = g;
+  r.vec8 = sizeof(T) == 2 && g.W % 8 == 0;
+  for (int l = 0; r.vec8 && l < g.L && l < kMaxTiledLayers; ++l) {
+    const SrcLayer& a = src.s[l];
+    if (a.w % 8 || a.left % 8 || a.sh % 8 || a.sc % 8 || a.sb % 8 || reinterpret_cast<uintptr_t>(a.ptr) % 16) r.vec8 = 0;
+  }
+  return r;
+}
+
 template <typename T, bool kRagged>
 int launch_forward_tiled(const void* x, const SrcLayers& src, const float* theta, void* out, void* sav, const mgr::Geometry& g,
                          cudaStream_t s) {
@@ -87,6 +123,26 @@ int launch_forward_tiled(const void* x, const SrcLayers& src, const float* theta
   dim3 grid((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B);
   using SA = typename SavedAlpha<T>::type;
   const int stencil = debug_path() != 2;        // all-translation samples take the stencil path
+  if (debug_path() != 3) {
+    // warp-specialised general path (render_ws.cuh) + the stencil kernel for all-translation samples; every CTA of
+    // either launch reads its sample's placements and leaves at once if the sample is the other kernel's
+    const size_t smem_w = ws_fwd_smem_bytes(g.L, sizeof(Vec));
+    auto launch = [&](auto kern) -> int {
+      if (int rc = ensure_dynamic_smem(kern, smem_w)) return rc;
+      kern<<<grid, kWsThreads, smem_w, s>>>((const T*)x, src, theta, (T*)out, (SA*)sav, with_vec8<T>(src, g), stencil);
+      return MGR_OK;
+    };
+    if (int rc = sav ? launch(render_fwd_ws<T, true, kRagged>) : launch(render_fwd_ws<T, false, kRagged>)) return rc;
+    if (stencil) {
+      MGR_CUDA(cudaGetLastError());
+      count_launch();
+      if (sav) render_fwd_stencil_only<T, true><<<grid, kTiledThreads, smem_b, s>>>(src, theta, (T*)out, (SA*)sav, g);
+      else render_fwd_stencil_only<T, false><<<grid, kTiledThreads, smem_b, s>>>(src, theta, (T*)out, nullptr, g);
+    }
+    MGR_CUDA(cudaGetLastError());
+    count_launch();
+    return MGR_OK;
+  }
   if constexpr (sizeof(T) == 4) {               // fp32: one launch per path (see render_fwd.cuh)
     if (sav) render_fwd_general_only<T, true, kRagged><<<grid, kTiledThreads, smem_a, s>>>((const T*)x, src, theta, (T*)out, (SA*)sav, g, stencil);
     else render_fwd_general_only<T, false, kRagged><<<grid, kTiledThreads, smem_a, s>>>((const T*)x, src, theta, (T*)out, nullptr, g, stencil);
@@ -183,18 +239,34 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
     MGR_CUDA(cudaGetLastError());
     count_launch(2);
   }
-  size_t smem = align16(tiled_smem_bytes(g.L, sizeof(Vec))) +
-                sizeof(float) * (size_t)g.L * kPx * kTiledThreads;                // + transmittance stash
-  // (G_P, G_A) copy in shared memory if two CTAs per SM still fit (the kernels are compiled for two: at three they
-  // spill, and the spills cost more than the third CTA hides)
-  const size_t gp_bytes = sizeof(float4) * kPx * kTiledThreads;
-  const bool gp_smem = (smem + gp_bytes) * 2 + 2 * 1024 <= 227 * 1024;
-  if (gp_smem) smem += gp_bytes;
   dim3 grid((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B);
   const int shift = debug_path() != 2;
-  {
+  const size_t gp_bytes = sizeof(float4) * kPx * kTiledThreads;
+  // warp-specialised pass 1 for 16-bit tensors; fp32 keeps the two-barrier kernel (its 45 KB slots leave room for one
+  // CTA per SM only next to the transmittance stash: measured 4-12 % slower)
+  if (debug_path() != 3 && sizeof(T) == 2) {
+    // warp-specialised pass 1 (render_ws.cuh); (G_P, G_A) copy in shared memory if two CTAs per SM still fit
+    const bool gp_smem = ws_bwd_smem_bytes(g.L, sizeof(Vec), true) * MGR_WSB_BLOCKS + 2 * 1024 <= 227 * 1024;
+    const size_t smem = ws_bwd_smem_bytes(g.L, sizeof(Vec), gp_smem);
     auto launch = [&](auto kern) -> int {
-      MGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      if (int rc = ensure_dynamic_smem(kern, smem)) return rc;
+      kern<<<grid, kWsThreads, smem, s>>>((const T*)x, src, theta, (const T*)out, (const T*)gout, (const SA*)sav, rec, gp,
+                                          nt ? gtheta : nullptr, with_vec8<T>(src, g), sflag, shift);
+      return MGR_OK;
+    };
+    int rc;
+    if (nt) rc = gp_smem ? launch(render_bwd_pass1_ws<T, true, true, kRagged>) : launch(render_bwd_pass1_ws<T, true, false, kRagged>);
+    else rc = gp_smem ? launch(render_bwd_pass1_ws<T, false, true, kRagged>) : launch(render_bwd_pass1_ws<T, false, false, kRagged>);
+    if (rc) return rc;
+  } else {
+    size_t smem = align16(tiled_smem_bytes(g.L, sizeof(Vec))) +
+                  sizeof(float) * (size_t)g.L * kPx * kTiledThreads;                // + transmittance stash
+    // (G_P, G_A) copy in shared memory if two CTAs per SM still fit (the kernels are compiled for two: at three they
+    // spill, and the spills cost more than the third CTA hides)
+    const bool gp_smem = (smem + gp_bytes) * 2 + 2 * 1024 <= 227 * 1024;
+    if (gp_smem) smem += gp_bytes;
+    auto launch = [&](auto kern) -> int {
+      if (int rc = ensure_dynamic_smem(kern, smem)) return rc;
       kern<<<grid, kTiledThreads, smem, s>>>((const T*)x, src, theta, (const T*)out, (const T*)gout, (const SA*)sav, rec, gp,
                                              nt ? gtheta : nullptr, g, sflag, shift);
       return MGR_OK;
@@ -225,7 +297,7 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
     if (gp_smem3) smem3 += gp_bytes;
     dim3 grid3((g.W + 1 + kAnchor - 1) / kAnchor, (g.H + 1 + kAnchor - 1) / kAnchor, g.B);
     auto launch3 = [&](auto kern) -> int {
-      MGR_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      if (int rc = ensure_dynamic_smem(kern, smem3)) return rc;
       kern<<<grid3, kTiledThreads, smem3, s>>>(src, theta, (const T*)out, (const T*)gout, (const SA*)sav, dst,
                                                nt ? gtheta : nullptr, gp, g, sflag);
       return MGR_OK;
@@ -339,7 +411,7 @@ int launch_warp_backward(const void* x, const float* theta, const void* gout, vo
     if (nt) {
       MGR_CUDA(cudaMemsetAsync(gtheta, 0, sizeof(float) * 6 * g.B * g.L, s));
       const size_t smem = sizeof(Vec) * kCapTexels + sizeof(float) * kPx * kTiledThreads;
-      MGR_CUDA(cudaFuncSetAttribute(warp_bwd_theta_tiled<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+      if (int rc = ensure_dynamic_smem(warp_bwd_theta_tiled<T>, smem)) return rc;
       dim3 gridt((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B * g.L);
       warp_bwd_theta_tiled<T><<<gridt, kTiledThreads, smem, s>>>((const T*)x, theta, (const T*)gout, gtheta, g);
       MGR_CUDA(cudaGetLastError());

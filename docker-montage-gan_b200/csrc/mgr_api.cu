@@ -52,6 +52,7 @@ int check_common(const void* x, const int64_t* xs, int B, int L, int H, int W, i
   if (L > 32) return fail(MGR_ERR_UNSUPPORTED, "L=%d exceeds 32 layers", L);
   g->B = B; g->L = L; g->H = H; g->W = W;
   g->m11 = (range_mode == MGR_RANGE_M11);
+  g->vec8 = 0;
   if (xs) {
     if (xs[4] != 1) return fail(MGR_ERR_UNSUPPORTED, "x stride along W must be 1 (got %lld)", (long long)xs[4]);
     g->sb = xs[0]; g->sl = xs[1]; g->sc = xs[2]; g->sh = xs[3];
@@ -79,7 +80,7 @@ const char* mgr_build_info(void) {
 const char* mgr_last_error(void) { return g_err; }
 
 int mgr_set_debug_path(int path) {
-  if (path < 0 || path > 2) return fail(MGR_ERR_INVALID_ARGUMENT, "debug path %d unknown", path);
+  if (path < 0 || path > 3) return fail(MGR_ERR_INVALID_ARGUMENT, "debug path %d unknown", path);
   g_debug_path.store(path, std::memory_order_relaxed);
   return MGR_OK;
 }
@@ -248,6 +249,7 @@ int ragged_geometry(const MgrLayer* layers, const float* theta, int B, int L, in
   if ((long long)B * L > 65535) return fail(MGR_ERR_UNSUPPORTED, "B*L=%lld exceeds 65535 per call; split the batch", (long long)B * L);
   g->B = B; g->L = L; g->H = H; g->W = W;
   g->m11 = (range_mode == MGR_RANGE_M11);
+  g->vec8 = 0;
   g->sh = W; g->sc = (long long)H * W; g->sl = 4 * g->sc; g->sb = (long long)L * g->sl;     // unused by the ragged kernels
   *src = mgr::SrcLayers{};
   for (int l = 0; l < L; ++l)

@@ -27,6 +27,7 @@ struct Geometry {
   int B, L, H, W;
   long long sb, sl, sc, sh;  // element strides of x for [B,L,4,H,W]; W stride is 1
   int m11;                   // 1: [-1,1] range mode, 0: [0,1]
+  int vec8;                  // warp-specialised kernels: 16-bit footprints staged in 8-texel items (set by the launchers)
 };
 
 // kVec adjacent elements -> fp32 (kVec = 4: one 16- or 8-byte load; the caller guarantees the alignment)

@@ -31,7 +31,8 @@ template <typename T, bool kSave>
 __global__ void __launch_bounds__(kTiledThreads, MGR_SHF_BLOCKS)
 render_fwd_stencil_only(const __grid_constant__ SrcLayers src, const float* __restrict__ theta, T* __restrict__ out,
                         typename SavedAlpha<T>::type* __restrict__ sav, Geometry g) {
-  if (!cta_all_shift(theta + (long long)blockIdx.z * g.L * 6, g.L, threadIdx.x, kTiledThreads)) return;
+  // every warp finds out by itself whether the sample is this kernel's (no CTA barrier before an idle CTA leaves)
+  if (!__all_sync(0xffffffffu, (int)(threadIdx.x & 31) >= g.L || is_pure_shift(theta + ((long long)blockIdx.z * g.L + (threadIdx.x & 31)) * 6))) return;
   fwd_shift_body<T, kSave>(src, theta, out, sav, g);
 }
 

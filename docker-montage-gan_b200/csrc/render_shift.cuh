@@ -55,7 +55,7 @@ __device__ __forceinline__ LayerPlan shift_footprint(const ShiftPlan& sp, int j0
   p.bh = kTH + 1;
   const bool miss = (p.x_lo + p.bw <= src.left) || (p.x_lo >= src.left + src.w) || (p.y_lo + p.bh <= src.top) || (p.y_lo >= src.top + src.h);
   p.mode = miss ? kSkip : kStaged;
-  p.lrx = p.lry = 0.f; p.pad_ = 0;
+  p.lrx = p.lry = 0.f; p.pitch = p.bw; p.dX = p.dY = 0; p.pad2_[0] = p.pad2_[1] = 0;
   return p;
 }
 

@@ -39,7 +39,9 @@ struct LayerPlan {
   int x_lo, y_lo;   // footprint origin in the source image (x_lo multiple of the staging vector width)
   int bw, bh;       // footprint size in texels (bw multiple of the vector width) == shared pitch / rows
   int mode;
-  int pad_;
+  int pitch;        // warp-specialised kernels: row pitch of the staged footprint in texels (>= bw)
+  int dX, dY;       // staged path: tap column / row inside the footprint = floor(tile-centre-relative coordinate) + (dX, dY)
+  int pad2_[2];
 };
 
 // One layer's pixels for the CTA's sample: SrcLayer with the batch offset applied and byte strides (they fit 32 bits,
@@ -102,7 +104,7 @@ __device__ __forceinline__ LayerPlan plan_layer(const float* __restrict__ th, in
   const float ymax = t.ry + fmaxf(t.a10 * lo_, t.a10 * hi_) + fmaxf(t.a11 * lov, t.a11 * hiv) + eps;
   p.x_lo = p.y_lo = p.bw = p.bh = 0;
   p.lrx = p.lry = 0.f;
-  p.pad_ = 0;
+  p.pitch = 0; p.dX = p.dY = 0; p.pad2_[0] = p.pad2_[1] = 0;
   p.mode = kDirect;
   // NaN / huge placements take the bounds-checked direct path
   // (the direct path addresses the layer's own pixels: origin moved to the rectangle's corner)
@@ -114,12 +116,17 @@ __device__ __forceinline__ LayerPlan plan_layer(const float* __restrict__ th, in
   int y_lo = Y0 + (int)floorf(ymin), y_hi = Y0 + (int)floorf(ymax) + 1;
   // the taps miss the layer's rectangle: a fully transparent layer for this tile
   if (x_hi < src.left || x_lo >= src.left + src.w || y_hi < src.top || y_lo >= src.top + src.h) { p.mode = kSkip; return p; }
+  // staged or direct: decided on the footprint as the WIDEST staging vector (8 texels) would lay it out, so that the
+  // decision -- and with it the arithmetic that produces every bit of the result -- does not depend on the alignment
+  // the tensor happens to allow (a ragged stack and its padded canvas must agree bit for bit)
+  const int bw8 = (x_hi - (x_lo & ~7) + 8) & ~7;
   x_lo &= ~(vec - 1);                                   // vec = staging vector width in texels (4 or 8)
   const int bw = (x_hi - x_lo + vec) & ~(vec - 1), bh = y_hi - y_lo + 1;
-  p.x_lo = x_lo; p.y_lo = y_lo; p.bw = bw; p.bh = bh;
+  p.x_lo = x_lo; p.y_lo = y_lo; p.bw = bw; p.bh = bh; p.pitch = bw;
   p.lrx = t.rx + (float)(X0 - x_lo);
   p.lry = t.ry + (float)(Y0 - y_lo);
-  p.mode = ((long long)bw * bh <= kCapTexels) ? kStaged : kDirect;
+  p.dX = X0 - x_lo; p.dY = Y0 - y_lo;
+  p.mode = ((long long)bw8 * bh <= kCapTexels) ? kStaged : kDirect;
   return p;
 }
 

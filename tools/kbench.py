@@ -59,7 +59,7 @@ def main():
             sav = torch.empty(max(lib.mgr_saved_alpha_bytes(B, L, H, W, dt), 1), dtype=torch.uint8, device=dev)
             sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
             for path in args.paths.split(","):
-                lib.mgr_set_debug_path({"auto": 0, "direct": 1}[path])
+                lib.mgr_set_debug_path({"auto": 0, "direct": 1, "nostencil": 2, "legacy": 3}[path])
                 def fwd(k):
                     _lib.check(lib.mgr_render_forward(P(xs[k]), None, P(ths[k]), P(out), P(sav), B, L, H, W, dt, 0, sp), "fwd")
                 def bwd(k):
