@@ -397,7 +397,9 @@ template <> struct Pack2<__half> {
   }
 };
 
-__device__ __forceinline__ float hat(float u) { return fmaxf(1.f - fabsf(u), 0.f); }
+// hat(u) = max(0, 1 - |u|): one FADD.SAT (1 - |u| never exceeds 1, so the upper clamp of the saturation is idle; a NaN
+// coordinate yields 0 instead of NaN -- such placements are flagged invalid before the loops anyway)
+__device__ __forceinline__ float hat(float u) { return __saturatef(1.f - fabsf(u)); }
 
 #ifndef MGR_P2_BLOCKS
 #define MGR_P2_BLOCKS 4
@@ -414,11 +416,10 @@ struct CompositeRecords {
   }
   __device__ __forceinline__ CompositeRecords at(int off) const { return CompositeRecords{r + off, g + off}; }
   __device__ __forceinline__ void advance(int off) { r += off; g += off; }
-  __device__ __forceinline__ void load(int mm, f32x2& grg, f32x2& gba) const {
+  __device__ __forceinline__ void load(int mm, float (&gv)[4]) const {
     const float2 rr = __ldg(r + mm);
     const float4 G = __ldg(g + mm);
-    grg = pk(G.x * rr.x, G.y * rr.x);
-    gba = pk(G.z * rr.x, rr.y);
+    gv[0] = G.x * rr.x; gv[1] = G.y * rr.x; gv[2] = G.z * rr.x; gv[3] = rr.y;
   }
 };
 template <typename T>
@@ -428,9 +429,8 @@ struct PlanarGrads {
   __device__ __forceinline__ PlanarGrads layer(int n, int, int hw_) const { return PlanarGrads{p + (long long)n * 4 * hw_, hw_}; }
   __device__ __forceinline__ PlanarGrads at(int off) const { return PlanarGrads{p + off, hw}; }
   __device__ __forceinline__ void advance(int off) { p += off; }
-  __device__ __forceinline__ void load(int mm, f32x2& grg, f32x2& gba) const {
-    grg = pk(ld(p + mm), ld(p + hw + mm));
-    gba = pk(ld(p + 2 * hw + mm), ld(p + 3 * hw + mm));
+  __device__ __forceinline__ void load(int mm, float (&gv)[4]) const {
+    gv[0] = ld(p + mm); gv[1] = ld(p + hw + mm); gv[2] = ld(p + 2 * hw + mm); gv[3] = ld(p + 3 * hw + mm);
   }
 };
 
@@ -457,9 +457,20 @@ __device__ __forceinline__ void pass2_block(const InverseLayer* __restrict__ pla
   // CTA-uniform: the whole 64 x 16 texel block lies outside this layer's rectangle (small layers of a ragged stack)
   if (x0b + kP2W <= dl.left || x0b >= dl.left + dl.w || y0b + kP2H <= dl.top || y0b >= dl.top + dl.h) return;
   T* gxp = reinterpret_cast<T*>(dl.ptr) + (long long)b * dl.sb + (long long)yl * dl.sh + xl;
-  f32x2 acc[2][2][2];                           // [row][col][rg | ba]
+  // acc[row][channel] = (texel column 0, texel column 1): the two columns share the candidate's gradient value, so a
+  // candidate costs eight packed FMAs whose scalar operand is the gradient and whose pair operand is (w_y * w_x0, w_y * w_x1)
+  f32x2 acc[2][4];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) (&acc[0][0][0])[q] = 0ull;
+  for (int q = 0; q < 8; ++q) (&acc[0][0])[q] = 0ull;
+  auto accumulate = [](f32x2 (&a)[2][4], float wx0, float wx1, float wy0, float wy1, const float (&gv)[4]) {
+    const f32x2 wx = pk(wx0, wx1);
+    const f32x2 w0 = mul2(wx, bc(wy0)), w1 = mul2(wx, bc(wy1));
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      a[0][c] = fma2(bc(gv[c]), w0, a[0][c]);
+      a[1][c] = fma2(bc(gv[c]), w1, a[1][c]);
+    }
+  };
 
   if (L_.shift_only) {
     // pure translation: texel (x, y) is tap (dx, dy) of pixel (x - X - dx, y - Y - dy) with the layer-wide
@@ -474,21 +485,12 @@ __device__ __forceinline__ void pass2_block(const InverseLayer* __restrict__ pla
       for (int dj = -1; dj <= 1; ++dj) {
         const int j = x - L_.X + dj;
         if ((unsigned)j >= (unsigned)g.W) continue;
-        f32x2 grg, gba;
-        src.layer(n, b, hw).load(i * g.W + j, grg, gba);
-#pragma unroll
-        for (int ky = 0; ky < 2; ++ky) {
-          const int ty_ = ky - di;              // tap row index of texel row ky for this pixel: (y + ky) - (i + Y)
-          if (ty_ < 0 || ty_ > 1) continue;
-#pragma unroll
-          for (int kx = 0; kx < 2; ++kx) {
-            const int tx_ = kx - dj;
-            if (tx_ < 0 || tx_ > 1) continue;
-            const f32x2 w2 = bc(wy[ty_] * wx[tx_]);
-            acc[ky][kx][0] = fma2(w2, grg, acc[ky][kx][0]);
-            acc[ky][kx][1] = fma2(w2, gba, acc[ky][kx][1]);
-          }
-        }
+        float gv[4];
+        src.layer(n, b, hw).load(i * g.W + j, gv);
+        // tap index of texel (row ky, column kx) for this pixel: (ky - di, kx - dj), weight 0 outside {0, 1}
+        const float ux0 = (dj == 0) ? wx[0] : (dj == -1 ? wx[1] : 0.f), ux1 = (dj == 1) ? wx[0] : (dj == 0 ? wx[1] : 0.f);
+        const float uy0 = (di == 0) ? wy[0] : (di == -1 ? wy[1] : 0.f), uy1 = (di == 1) ? wy[0] : (di == 0 ? wy[1] : 0.f);
+        accumulate(acc, ux0, ux1, uy0, uy1, gv);
       }
     }
   } else {
@@ -522,7 +524,7 @@ __device__ __forceinline__ void pass2_block(const InverseLayer* __restrict__ pla
     const Src src0 = src.layer(n, b, hw).at(IC * g.W + JC);
 
     // one candidate row nn of the window (mlo_..mhi_) of the block at (x0l_, y0l_), accumulated into acc_
-    auto row = [&](int nn, float mlo_, float mhi_, float x0l_, float y0l_, f32x2 (&acc_)[2][2][2]) {
+    auto row = [&](int nn, float mlo_, float mhi_, float x0l_, float y0l_, f32x2 (&acc_)[2][4]) {
       const float di = (float)nn - icf;
       const float ub = fmaf(a01, di, -x0l_), vb = fmaf(a11, di, -y0l_);
       float lo = mlo_, hi = mhi_;
@@ -549,14 +551,9 @@ __device__ __forceinline__ void pass2_block(const InverseLayer* __restrict__ pla
       const Src cur = src0.at(nn * g.W);
 #pragma unroll 1
       for (int mm = ma; mm <= mb; ++mm, u += a00, v += a10) {
-        const float wx0 = hat(u), wx1 = hat(u - 1.f), wy0 = hat(v), wy1 = hat(v - 1.f);
-        f32x2 grg, gba;
-        cur.load(mm, grg, gba);
-        const f32x2 w00 = bc(wy0 * wx0), w01 = bc(wy0 * wx1), w10 = bc(wy1 * wx0), w11 = bc(wy1 * wx1);
-        acc_[0][0][0] = fma2(w00, grg, acc_[0][0][0]); acc_[0][0][1] = fma2(w00, gba, acc_[0][0][1]);
-        acc_[0][1][0] = fma2(w01, grg, acc_[0][1][0]); acc_[0][1][1] = fma2(w01, gba, acc_[0][1][1]);
-        acc_[1][0][0] = fma2(w10, grg, acc_[1][0][0]); acc_[1][0][1] = fma2(w10, gba, acc_[1][0][1]);
-        acc_[1][1][0] = fma2(w11, grg, acc_[1][1][0]); acc_[1][1][1] = fma2(w11, gba, acc_[1][1][1]);
+        float gv[4];
+        cur.load(mm, gv);
+        accumulate(acc_, hat(u), hat(u - 1.f), hat(v), hat(v - 1.f), gv);
       }
     };
 
@@ -575,24 +572,24 @@ __device__ __forceinline__ void pass2_block(const InverseLayer* __restrict__ pla
         for (int nn = n0; nn <= n1; ++nn, di += 1.f) {
           float u = fmaf(a00, dj0, fmaf(a01, di, -x0l));
           float v = fmaf(a10, dj0, fmaf(a11, di, -y0l));
+          if constexpr (kComposite) {
 #pragma unroll 1
-          for (int mm = m0; mm <= m1; ++mm, u += a00, v += a10) {
-            const float wx0 = hat(u), wx1 = hat(u - 1.f), wy0 = hat(v), wy1 = hat(v - 1.f);
-            f32x2 grg, gba;
-            if constexpr (kComposite) {
+            for (int mm = m0; mm <= m1; ++mm, u += a00, v += a10) {
               const float2 r = __ldg(recn + mm);
               const float4 G = __ldg(gpb + mm);
-              grg = pk(G.x * r.x, G.y * r.x); gba = pk(G.z * r.x, r.y);
-            } else {
-              cur.load(mm, grg, gba);
+              const float gv[4] = {G.x * r.x, G.y * r.x, G.z * r.x, r.y};
+              accumulate(acc, hat(u), hat(u - 1.f), hat(v), hat(v - 1.f), gv);
             }
-            const f32x2 w00 = bc(wy0 * wx0), w01 = bc(wy0 * wx1), w10 = bc(wy1 * wx0), w11 = bc(wy1 * wx1);
-            acc[0][0][0] = fma2(w00, grg, acc[0][0][0]); acc[0][0][1] = fma2(w00, gba, acc[0][0][1]);
-            acc[0][1][0] = fma2(w01, grg, acc[0][1][0]); acc[0][1][1] = fma2(w01, gba, acc[0][1][1]);
-            acc[1][0][0] = fma2(w10, grg, acc[1][0][0]); acc[1][0][1] = fma2(w10, gba, acc[1][0][1]);
-            acc[1][1][0] = fma2(w11, grg, acc[1][1][0]); acc[1][1][1] = fma2(w11, gba, acc[1][1][1]);
+            recn += g.W; gpb += g.W;
+          } else {
+#pragma unroll 1
+            for (int mm = m0; mm <= m1; ++mm, u += a00, v += a10) {
+              float gv[4];
+              cur.load(mm, gv);
+              accumulate(acc, hat(u), hat(u - 1.f), hat(v), hat(v - 1.f), gv);
+            }
+            cur.advance(g.W);
           }
-          if constexpr (kComposite) { recn += g.W; gpb += g.W; } else { cur.advance(g.W); }
         }
       }
     } else {
@@ -608,20 +605,20 @@ __device__ __forceinline__ void pass2_block(const InverseLayer* __restrict__ pla
         const float mlo_s = __shfl_sync(0xffffffffu, mlo, src), mhi_s = __shfl_sync(0xffffffffu, mhi, src);
         const int n0_s = (int)__shfl_sync(0xffffffffu, nlo, src), n1_s = (int)__shfl_sync(0xffffffffu, nhi, src);
         const float x0l_s = __shfl_sync(0xffffffffu, x0l, src), y0l_s = __shfl_sync(0xffffffffu, y0l, src);
-        f32x2 part[2][2][2];
+        f32x2 part[2][4];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) (&part[0][0][0])[q] = 0ull;
+        for (int q = 0; q < 8; ++q) (&part[0][0])[q] = 0ull;
         for (int nn = n0_s + lane; nn <= n1_s; nn += 32) row(nn, mlo_s, mhi_s, x0l_s, y0l_s, part);
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           float p0, p1;
-          upk((&part[0][0][0])[q], p0, p1);
+          upk((&part[0][0])[q], p0, p1);
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
             p0 += __shfl_xor_sync(0xffffffffu, p0, o);
             p1 += __shfl_xor_sync(0xffffffffu, p1, o);
           }
-          if (lane == src) (&acc[0][0][0])[q] = pk(p0, p1);
+          if (lane == src) (&acc[0][0])[q] = pk(p0, p1);
         }
       }
       if (has && !heavy) {
@@ -634,14 +631,13 @@ __device__ __forceinline__ void pass2_block(const InverseLayer* __restrict__ pla
 #pragma unroll
   for (int ky = 0; ky < 2; ++ky) {
     if ((unsigned)(yl + ky) >= (unsigned)dl.h) continue;
-    float r0, g0, b0, a0, r1, g1, b1, a1;
-    upk(acc[ky][0][0], r0, g0); upk(acc[ky][0][1], b0, a0);
-    upk(acc[ky][1][0], r1, g1); upk(acc[ky][1][1], b1, a1);
     T* o = gxp + ky * dl.sh;
-    Pack2<T>::store(o, zs * r0, zs * r1);              // w % 4 == 0 and left % 4 == 0 on this path: xl + 1 < w
-    Pack2<T>::store(o + dl.sc, zs * g0, zs * g1);
-    Pack2<T>::store(o + 2 * dl.sc, zs * b0, zs * b1);
-    Pack2<T>::store(o + 3 * dl.sc, zs * a0, zs * a1);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      float t0, t1;                                    // texel columns 0 and 1 of channel c
+      upk(acc[ky][c], t0, t1);
+      Pack2<T>::store(o + c * dl.sc, zs * t0, zs * t1);    // w % 4 == 0 and left % 4 == 0 on this path: xl + 1 < w
+    }
   }
 }
 
