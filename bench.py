@@ -143,7 +143,7 @@ def run_reference_arm(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample_B = min(B, 8)
+    sample_B = B                              # the whole batch of the workload: same config as the CUDA arm
     t0 = time.perf_counter()
     base, times = cpu_reference_throughput(L, H, W, sample_B, min_seconds=0.0, max_iters=args.steps + args.warmup)
     times = times[-args.steps:] if len(times) > args.steps else times
@@ -152,8 +152,9 @@ def run_reference_arm(args, wl):
     base["value"] = value
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": desc + f"; CPU arm runs a B={sample_B} sample per step in fp32",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "storage_dtype": "float32", "data": "synthetic",
+            "config": {"workload": desc + f"; the CPU arm runs the whole batch (B={sample_B}) per step, fp32 storage and arithmetic "
+                                          "as the reference computes",
                        "theta": "I + 0.25*N(0,1), covering back layer", "layers": "smooth (S) family"},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -262,6 +263,35 @@ def run_cuda_arm(args, wl):
     _, ms_T, thr_T = sharding.aggregate_throughput(units_per_step * args.steps, t0e.elapsed_time(t1e), dev)
     ths[:] = ths_I
 
+    # ---- the same workload with fp32 STORAGE (what the CPU arm computes on), kernels only -------------------------
+    thr_32, ms_32 = None, None
+    if dtype != torch.float32 and not args.kernels_only:
+        x32 = xs[0].float()
+        go32 = gos[0].float()
+        out32 = torch.empty((B, 4, H, W), dtype=torch.float32, device=dev)
+        gx32 = torch.empty((B, L, 4, H, W), dtype=torch.float32, device=dev)
+        ws32_bytes = lib.mgr_render_backward_workspace_bytes(B, L, H, W, 0, 1, flags)
+        ws32 = torch.empty(max(ws32_bytes, 1), dtype=torch.uint8, device=dev)
+        sav32 = torch.empty(max(lib.mgr_saved_alpha_bytes(B, L, H, W, 0), 1), dtype=torch.uint8, device=dev)
+
+        def step32(k):
+            _lib.check(lib.mgr_render_forward(P(x32), None, P(ths[k]), P(out32), P(sav32), B, L, H, W, 0, 0, sp), "forward fp32")
+            _lib.check(lib.mgr_render_backward(P(x32), None, P(ths[k]), P(out32), P(go32), P(sav32), P(gx32), P(gt), P(ws32),
+                                               ws32_bytes, B, L, H, W, 0, 0, flags, sp), "backward fp32")
+        n32 = max(3, min(args.steps, 10))
+        for i in range(3):
+            step32(i % NSETS)
+        torch.cuda.synchronize(dev)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for i in range(n32):
+            step32(i % NSETS)
+        a1.record(stream)
+        torch.cuda.synchronize(dev)
+        _, ms_32, thr_32 = sharding.aggregate_throughput(units_per_step * n32, a0.elapsed_time(a1), dev)
+        ms_32 /= n32
+        del x32, go32, out32, gx32, ws32, sav32
+
     # ---- end to end through the C ABI with pinned HOST buffers (H2D + kernels + D2H in the timed region) ----
     e2e_steps = 0 if args.kernels_only else max(3, min(args.steps, 10))
     e2e_value, h2d, d2h = None, 0, 0
@@ -290,34 +320,47 @@ def run_cuda_arm(args, wl):
         fb, bb = algorithmic_bytes(B, L, H, W, es, es, es)
         # dominant kernel = the backward pass (scatter + theta reduction)
         achieved = bb / 1e9 / (bwd_ms / 1e3)
-        roofline = {"bound": "hbm", "kernel": "render backward (mgr_render_backward)", "achieved": achieved,
-                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": (measured_traffic(args.workload) or {}).get("bytes"),
-                    "traffic_source": (measured_traffic(args.workload) or {}).get("source"), "peak_source": peak_src,
+        tr = measured_traffic(args.workload) or {}
+        roofline = {"bound": "hbm", "kernel": "render backward (mgr_render_backward: placements + pass 1 + pass 2)", "achieved": achieved,
+                    "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": tr.get("bytes"),
+                    "traffic_source": tr.get("source"), "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": bb,
                     "forward": {"achieved": fb / 1e9 / (fwd_ms / 1e3), "frac": fb / 1e9 / (fwd_ms / 1e3) / peak,
-                                "ms": fwd_ms, "algorithmic_bytes_per_launch": fb},
+                                "ms": fwd_ms, "algorithmic_bytes_per_launch": fb, "traffic": tr.get("forward")},
                     "backward_ms": bwd_ms,
                     "fwd_bwd": {"achieved": (fb + bb) / 1e9 / ((fwd_ms + bwd_ms) / 1e3),
                                 "frac": (fb + bb) / 1e9 / ((fwd_ms + bwd_ms) / 1e3) / peak,
                                 "frac_of_nominal_8TBs": (fb + bb) / 1e9 / ((fwd_ms + bwd_ms) / 1e3) / 8000.0}}
         cpu_base = None
         if not args.kernels_only:
-            cpu_base, _ = cpu_reference_throughput(L, H, W, min(B, 8), min_seconds=args.cpu_seconds, max_iters=50)
+            cpu_base, _ = cpu_reference_throughput(L, H, W, B if B * L * H * W <= 64 * 7 * 256 * 256 else min(B, 8),
+                                                   min_seconds=args.cpu_seconds, max_iters=50)
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": max_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "storage_dtype": dtype_name, "data": "synthetic",
                 "config": {"workload": desc + " per GPU, fp32 arithmetic in registers",
+                           "dtype_note": f"`dtype` is the arithmetic type (every sample, lerp and composite is fp32); tensors are stored as {dtype_name}",
                            "theta": "I + 0.25*N(0,1), covering back layer", "layers": "smooth (S) family",
                            "l2": f"{NSETS} rotating input sets of {xs[0].numel() * es / 1e6:.0f} MB each (> 126 MB L2)",
                            "sharding": f"batch-sharded, {B} samples per GPU, no data-path collective"},
                 "roofline": roofline, "cpu_baseline": cpu_base,
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "steps": e2e_steps, "api": "mgr_render_fwd_bwd_host (C ABI, pinned host buffers, "
-                                                   f"chunks of {args.chunk} samples on 3 streams)"},
+                                                   f"chunks of {args.chunk} samples on 3 streams)",
+                        "note": "bound by the host link, not the GPU: every step moves h2d + d2h bytes over PCIe (about 55 GB/s "
+                                "one way, 40-49 GB/s each way when both directions run, tools/pcie_peak.py); at N > 1 the ranks "
+                                "share the host's PCIe root complexes and DRAM, so e2e scales far below the kernels (SCALE_r01: "
+                                "1.8x at 8 GPUs against 7.7x device-resident)"},
                 "translation_only": {"value": thr_T / 1e6, "unit": UNIT, "ms_per_step": ms_T / args.steps,
                                      "frac": (fb + bb) / 1e9 / (ms_T / args.steps / 1e3) / peak,
+                                     "traffic": tr.get("translation_fwd_bwd"),
                                      "note": "same workload with the placements STNv2c emits (pure translations, "
                                              "U(-1,1)); kernels only, inputs resident"},
+                "fp32_storage": None if thr_32 is None else {
+                    "value": thr_32 / 1e6, "unit": UNIT, "ms_per_step": ms_32,
+                    "frac": sum(algorithmic_bytes(B, L, H, W, 4, 4, 4)) / 1e9 / (ms_32 / 1e3) / peak,
+                    "note": "the same batch and placements with fp32 tensors (the storage the CPU arm computes on; one input set "
+                            f"of {B * L * 4 * H * W * 4 / 1e6:.0f} MB > L2); kernels only, inputs resident"},
                 "gpu_launches": int(launches), "clocks": clocks.summary(),
                 "wall_s_timed_region": t_wall}
         print(json.dumps(line), flush=True)

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(PKG_DIR, "libmontage_render.so")
 MGR_F32, MGR_BF16, MGR_F16 = 0, 1, 2
 MGR_RANGE_M11, MGR_RANGE_01 = 0, 1
 MGR_NEED_GRAD_X, MGR_NEED_GRAD_THETA = 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _c = ctypes
 _vp, _i, _sz = _c.c_void_p, _c.c_int, _c.c_size_t
@@ -43,6 +43,7 @@ SYMBOLS = {
     "mgr_saved_alpha_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "mgr_render_forward": (_i, [_vp, _i64p, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mgr_render_backward_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
+    "mgr_render_backward_workspace_bytes_for": (_sz, [_vp, _i64p, _i, _i, _i, _i, _i, _i, _i, _i]),
     "mgr_warp_forward": (_i, [_vp, _i64p, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "mgr_warp_backward_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i]),
     "mgr_warp_backward": (_i, [_vp, _i64p, _vp, _vp, _vp, _vp, _vp, _sz, _i, _i, _i, _i, _i, _i, _i, _vp]),

@@ -498,6 +498,7 @@ int launch_backward_ragged(const SrcLayers& src, const float* theta, const void*
 
 #include "launchers_decl.h"
 #define MGR_INSTANTIATE(SUFFIX, T)                                                                           \
+  bool mgr_tiled_ok_##SUFFIX(const void* x, const mgr::Geometry& g) { return g.L >= 2 && mgr::tiled_ok<T>(x, g); } \
   int mgr_fwd_##SUFFIX(const void* x, const float* theta, void* out, void* sav, const mgr::Geometry& g,     \
                        cudaStream_t s) {                                                                     \
     return mgr::launch_forward<T>(x, theta, out, sav, g, s);                                                 \

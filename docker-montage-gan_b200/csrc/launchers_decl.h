@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include "mgr_common.cuh"
 #define MGR_DECLARE(SUFFIX)                                                                                  \
+  bool mgr_tiled_ok_##SUFFIX(const void* x, const mgr::Geometry& g);                                         \
   int mgr_fwd_##SUFFIX(const void* x, const float* theta, void* out, void* sav, const mgr::Geometry& g,     \
                        cudaStream_t s);                                                                      \
   int mgr_bwd_##SUFFIX(const void* x, const float* theta, const void* out, const void* gout, const void* sav, \

@@ -98,6 +98,9 @@ int mgr_render_forward(const void* x, const int64_t* x_strides, const float* the
   if (int rc = check_common(x, x_strides, B, L, H, W, dtype, range_mode, &g)) return rc;
   if (!out) return fail(MGR_ERR_INVALID_ARGUMENT, "out is NULL");
   if (B == 0) return MGR_OK;
+  // the backward of a warped stack addresses layers through a 16-bit grid dimension: refuse here, before any work is
+  // queued, what mgr_render_backward would refuse later
+  if (theta && (long long)B * L > 65535) return fail(MGR_ERR_UNSUPPORTED, "B*L=%lld exceeds 65535 per call; split the batch", (long long)B * L);
   cudaStream_t s = (cudaStream_t)stream;
   switch (dtype) {
     case MGR_F32: return mgr_fwd_f32(x, theta, out, saved_alpha, g, s);
@@ -106,17 +109,34 @@ int mgr_render_forward(const void* x, const int64_t* x_strides, const float* the
   }
 }
 
+namespace {
+// tiled two-pass path: fp32 records (T_l a_l, d a_l) per layer-pixel + G_P per pixel
+// + per layer: inverse plan (128 B), launch-order entry, work-list entry; + 4 counters; + a flag per sample
+size_t tiled_workspace(int B, int L, int H, int W) {
+  return ((size_t)B * L * H * W) * 8 + ((size_t)B * H * W) * 16 + (size_t)B * L * (128 + 4 + 4) + 32 + (size_t)B * 4;
+}
+}  // namespace
+
 size_t mgr_render_backward_workspace_bytes(int B, int L, int H, int W, int dtype, int has_theta, int flags) {
   if (B <= 0 || L <= 0 || H <= 0 || W <= 0 || !has_theta) return 0;
-  // tiled two-pass path: fp32 records (T_l a_l, d a_l) per layer-pixel + G_P per pixel
-  // + per layer: inverse plan (128 B), launch-order entry, work-list entry; + 4 counters; + a flag per sample
-  size_t need = ((size_t)B * L * H * W) * 8 + ((size_t)B * H * W) * 16 + (size_t)B * L * (128 + 4 + 4) + 32 + (size_t)B * 4;
+  size_t need = tiled_workspace(B, L, H, W);
   // general direct-gather path with 16-bit storage: fp32 scatter accumulator
   if ((flags & MGR_NEED_GRAD_X) && dtype != MGR_F32) {
     const size_t scatter = sizeof(float) * (size_t)B * L * 4 * H * W;
     if (scatter > need) need = scatter;
   }
   return need;
+}
+
+size_t mgr_render_backward_workspace_bytes_for(const void* x, const int64_t* x_strides, int has_theta, int has_saved_alpha,
+                                               int B, int L, int H, int W, int dtype, int flags) {
+  if (B <= 0 || L <= 0 || H <= 0 || W <= 0 || !has_theta) return 0;
+  mgr::Geometry g;
+  if (check_common(x, x_strides, B, L, H, W, dtype, MGR_RANGE_M11, &g) != MGR_OK) return 0;
+  const bool tiled = has_saved_alpha && (dtype == MGR_F32 ? mgr_tiled_ok_f32(x, g) : dtype == MGR_BF16 ? mgr_tiled_ok_bf16(x, g) : mgr_tiled_ok_f16(x, g));
+  if (tiled) return tiled_workspace(B, L, H, W);
+  if ((flags & MGR_NEED_GRAD_X) && dtype != MGR_F32) return sizeof(float) * (size_t)B * L * 4 * H * W;   // fp32 scatter accumulator
+  return 0;
 }
 
 int mgr_render_backward(const void* x, const int64_t* x_strides, const float* theta, const void* out,
@@ -131,9 +151,11 @@ int mgr_render_backward(const void* x, const int64_t* x_strides, const float* th
   if ((flags & MGR_NEED_GRAD_THETA) && !grad_theta)
     return fail(MGR_ERR_INVALID_ARGUMENT, "grad_theta is NULL but requested");
   if (!(flags & (MGR_NEED_GRAD_X | MGR_NEED_GRAD_THETA)) || B == 0) return MGR_OK;
-  const size_t need = mgr_render_backward_workspace_bytes(B, L, H, W, dtype, theta != nullptr, flags);
+  // what the path this call takes needs (the tiled kernels for aligned tensors with saved alphas, else the scatter path)
+  const size_t need = mgr_render_backward_workspace_bytes_for(x, x_strides, theta != nullptr, saved_alpha != nullptr, B, L, H, W, dtype, flags);
   if (need > 0 && (!workspace || workspace_bytes < need))
     return fail(MGR_ERR_WORKSPACE_TOO_SMALL, "workspace %zu bytes < required %zu", workspace_bytes, need);
+  if (theta && (long long)B * L > 65535) return fail(MGR_ERR_UNSUPPORTED, "B*L=%lld exceeds 65535 per call; split the batch", (long long)B * L);
   cudaStream_t s = (cudaStream_t)stream;
   switch (dtype) {
     case MGR_F32: return mgr_bwd_f32(x, theta, out, grad_out, saved_alpha, grad_x, grad_theta, workspace, g, flags, s);

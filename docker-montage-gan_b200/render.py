@@ -113,7 +113,9 @@ def _render_backward(xk, th, out, sav, grad_out, in_range, x_strides, need_x, ne
     gx = torch.empty((B, L, 4, H, W), dtype=xk.dtype, device=xk.device) if need_x else None
     gt = torch.empty((B, L, 2, 3), dtype=torch.float32, device=xk.device) if need_t else None
     dt = _DTYPES[xk.dtype]
-    ws_bytes = lib.mgr_render_backward_workspace_bytes(B, L, H, W, dt, int(th is not None), flags)
+    # what THIS tensor's path needs (the tiled kernels take about half of the upper bound for 16-bit tensors)
+    ws_bytes = lib.mgr_render_backward_workspace_bytes_for(_ptr(xk), x_strides, int(th is not None), int(sav is not None),
+                                                           B, L, H, W, dt, flags)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=xk.device) if ws_bytes else None
     with torch.cuda.device(xk.device):
         rc = lib.mgr_render_backward(_ptr(xk), x_strides, _ptr(th), _ptr(out), _ptr(go), _ptr(sav), _ptr(gx), _ptr(gt),

@@ -48,7 +48,7 @@
 extern "C" {
 #endif
 
-#define MGR_ABI_VERSION 3
+#define MGR_ABI_VERSION 4
 
 enum { MGR_F32 = 0, MGR_BF16 = 1, MGR_F16 = 2 };
 enum { MGR_RANGE_M11 = 0, MGR_RANGE_01 = 1 };
@@ -99,6 +99,14 @@ int mgr_render_forward(const void* x, const int64_t* x_strides, const float* the
  */
 size_t mgr_render_backward_workspace_bytes(int B, int L, int H, int W, int dtype, int has_theta,
                                            int flags);
+/*
+ * The same for ONE given tensor: knows from the pointer and the strides which kernels the call will take (the tiled
+ * two-pass kernels need about 8 bytes per layer-pixel, the scatter fallback for 16-bit tensors 16), so it is what a
+ * caller that allocates per call should ask; the function above is the upper bound over all layouts.
+ */
+size_t mgr_render_backward_workspace_bytes_for(const void* x, const int64_t* x_strides, int has_theta,
+                                               int has_saved_alpha, int B, int L, int H, int W, int dtype,
+                                               int flags);
 
 /*
  * Fused warp + composite, backward (the autograd of the chain above).

@@ -83,9 +83,19 @@ def test_backward_validation_and_workspace():
     assert lib.mgr_saved_alpha_bytes(2, 3, 8, 8, _lib.MGR_BF16) == 2 * 3 * 64 * 2
     need = lib.mgr_render_backward_workspace_bytes(2, 3, 8, 8, _lib.MGR_BF16, 1, 3)
     assert need == 2 * 3 * 4 * 64 * 4                # fp32 scatter accumulator of the general path dominates
+    # per-tensor query: an aligned bf16 tensor with saved alphas takes the tiled kernels (records only); without saved
+    # alphas, or from an odd address, the scatter path and its fp32 accumulator
+    tiled = 2 * 3 * 64 * 8 + 2 * 64 * 16 + 2 * 3 * (128 + 4 + 4) + 32 + 2 * 4
+    assert lib.mgr_render_backward_workspace_bytes_for(0x1000, None, 1, 1, 2, 3, 8, 8, _lib.MGR_BF16, 3) == tiled
+    assert lib.mgr_render_backward_workspace_bytes_for(0x1000, None, 1, 0, 2, 3, 8, 8, _lib.MGR_BF16, 3) == need
+    assert lib.mgr_render_backward_workspace_bytes_for(0x1002, None, 1, 1, 2, 3, 8, 8, _lib.MGR_BF16, 3) == need
+    assert lib.mgr_render_backward_workspace_bytes_for(0x1000, None, 0, 1, 2, 3, 8, 8, _lib.MGR_BF16, 3) == 0
     rc = lib.mgr_render_backward(0x1000, None, 0x3000, 0x2000, 0x2000, None, 0x4000, 0x5000, None, 0, 2, 3, 8, 8,
                                  _lib.MGR_BF16, 0, 3, None)
     assert rc == 3 and b"workspace" in lib.mgr_last_error()
+    # a warped stack of more than 65535 layers is refused by the forward already (the backward could not take it)
+    rc = lib.mgr_render_forward(0x1000, None, 0x3000, 0x2000, None, 40000, 2, 4, 4, 0, 0, None)
+    assert rc == 2 and b"65535" in lib.mgr_last_error()
     rc = lib.mgr_render_backward(0x1000, None, None, 0x2000, 0x2000, None, None, None, None, 0, 2, 3, 8, 8, 0, 0, 1, None)
     assert rc == 1                                   # grad_x requested but NULL
     rc = lib.mgr_render_backward(0x1000, None, None, 0x2000, 0x2000, None, None, None, None, 0, 2, 3, 8, 8, 0, 0, 0, None)

@@ -1,6 +1,12 @@
 #!/usr/bin/env python
-"""Write profiles/roofline_traffic.json from an `ncu --set full` report: DRAM bytes (read + write) per
-launch of the dominant kernel of the backward (pass 1 + pass 2 summed, one launch each per step).
+"""Write profiles/roofline_traffic.json from an `ncu --set full` report of `bench.py --kernels-only`: DRAM bytes (read +
+write) per launch of every kernel, averaged over its ACTIVE launches (a kernel whose samples belong to the other path
+leaves after one look at the placements: a few KB), and summed into the figures bench.py reports:
+
+    bytes                 backward, general placements   (placement kernels + pass 1 + pass 2)
+    forward               forward, general placements
+    translation_fwd_bwd   forward + backward of the translation-only leg (stencil kernels)
+
 Usage: python tools/update_traffic.py gpurun_out/prof.ncu-rep c2"""
 import csv
 import json
@@ -24,10 +30,24 @@ for r in rows[2:]:
     name = d["Kernel Name"].split("(")[0].replace("void ", "").replace("mgr::", "")
     b = sum(to_bytes(d[k], units[hdr.index(k)]) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
     per_kernel.setdefault(name, []).append(b)
-avg = {k: sum(v) / len(v) for k, v in per_kernel.items()}
-bwd = sum(v for k, v in avg.items() if "bwd" in k)
+# active launches of a kernel: within a factor 4 of its largest launch
+avg = {}
+for k, v in per_kernel.items():
+    act = [b for b in v if b * 4 >= max(v)]
+    avg[k] = sum(act) / len(act)
+
+
+def total(*keys):
+    return sum(v for k, v in avg.items() if any(s in k for s in keys))
+
+
 path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "roofline_traffic.json")
 data = json.load(open(path)) if os.path.exists(path) else {}
-data[workload] = {"bytes": bwd, "per_kernel": avg, "source": f"ncu --set full, {os.path.basename(rep)}: dram__bytes_read.sum + dram__bytes_write.sum per launch"}
+data[workload] = {
+    "bytes": total("render_bwd_pass1", "render_bwd_pass2", "placements", "inverse_plans", "sample_flags"),
+    "forward": total("render_fwd_ws", "render_fwd_general_only", "render_fwd<"),
+    "translation_fwd_bwd": total("render_fwd_stencil_only", "render_bwd_shift"),
+    "per_kernel": avg,
+    "source": f"ncu --set full, {os.path.basename(rep)}: dram__bytes_read.sum + dram__bytes_write.sum per active launch"}
 json.dump(data, open(path, "w"), indent=1)
 print(json.dumps(data[workload], indent=1))
