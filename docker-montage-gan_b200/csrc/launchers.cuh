@@ -127,17 +127,25 @@ int launch_forward_tiled(const void* x, const SrcLayers& src, const float* theta
     // warp-specialised general path (render_ws.cuh) + the stencil kernel for all-translation samples; every CTA of
     // either launch reads its sample's placements and leaves at once if the sample is the other kernel's
     const size_t smem_w = ws_fwd_smem_bytes(g.L, sizeof(Vec));
+    // per-sample "all translations" flags in the tail of the saved-alpha buffer (mgr_saved_alpha_bytes reserves it)
+    int* flags = nullptr;
+    if (stencil && sav) {
+      flags = reinterpret_cast<int*>(reinterpret_cast<char*>(sav) + saved_alpha_flags_offset(g.B, g.L, g.H, g.W, sizeof(SA)));
+      sample_shift_flags_kernel<<<(g.B + 255) / 256, 256, 0, s>>>(theta, g.B, g.L, flags);
+      MGR_CUDA(cudaGetLastError());
+      count_launch();
+    }
     auto launch = [&](auto kern) -> int {
       if (int rc = ensure_dynamic_smem(kern, smem_w)) return rc;
-      kern<<<grid, kWsThreads, smem_w, s>>>((const T*)x, src, theta, (T*)out, (SA*)sav, with_vec8<T>(src, g), stencil);
+      kern<<<grid, kWsThreads, smem_w, s>>>((const T*)x, src, theta, (T*)out, (SA*)sav, with_vec8<T>(src, g), stencil, flags);
       return MGR_OK;
     };
     if (int rc = sav ? launch(render_fwd_ws<T, true, kRagged>) : launch(render_fwd_ws<T, false, kRagged>)) return rc;
     if (stencil) {
       MGR_CUDA(cudaGetLastError());
       count_launch();
-      if (sav) render_fwd_stencil_only<T, true><<<grid, kTiledThreads, smem_b, s>>>(src, theta, (T*)out, (SA*)sav, g);
-      else render_fwd_stencil_only<T, false><<<grid, kTiledThreads, smem_b, s>>>(src, theta, (T*)out, nullptr, g);
+      if (sav) render_fwd_stencil_only<T, true><<<grid, kTiledThreads, smem_b, s>>>(src, theta, (T*)out, (SA*)sav, g, flags);
+      else render_fwd_stencil_only<T, false><<<grid, kTiledThreads, smem_b, s>>>(src, theta, (T*)out, nullptr, g, flags);
     }
     MGR_CUDA(cudaGetLastError());
     count_launch();
@@ -149,8 +157,8 @@ int launch_forward_tiled(const void* x, const SrcLayers& src, const float* theta
     if (stencil) {
       MGR_CUDA(cudaGetLastError());
       count_launch();
-      if (sav) render_fwd_stencil_only<T, true><<<grid, kTiledThreads, smem_b, s>>>(src, theta, (T*)out, (SA*)sav, g);
-      else render_fwd_stencil_only<T, false><<<grid, kTiledThreads, smem_b, s>>>(src, theta, (T*)out, nullptr, g);
+      if (sav) render_fwd_stencil_only<T, true><<<grid, kTiledThreads, smem_b, s>>>(src, theta, (T*)out, (SA*)sav, g, nullptr);
+      else render_fwd_stencil_only<T, false><<<grid, kTiledThreads, smem_b, s>>>(src, theta, (T*)out, nullptr, g, nullptr);
     }
   } else {
     if (sav) render_fwd<T, true, kRagged><<<grid, kTiledThreads, smem, s>>>((const T*)x, src, theta, (T*)out, (SA*)sav, g, stencil);

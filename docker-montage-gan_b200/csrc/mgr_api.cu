@@ -89,7 +89,9 @@ long long mgr_kernel_launch_count(void) { return g_launches.load(std::memory_ord
 
 size_t mgr_saved_alpha_bytes(int B, int L, int H, int W, int dtype) {
   if (B <= 0 || L <= 0 || H <= 0 || W <= 0) return 0;
-  return (size_t)B * L * H * W * (dtype == MGR_F32 ? 4 : 2);
+  // the alpha samples [B,L,H,W], then one int per sample: "all placements are pure translations" (written by the
+  // forward before its kernels run, so that a CTA learns with ONE load whether the sample is its kernel's)
+  return mgr::saved_alpha_flags_offset(B, L, H, W, dtype == MGR_F32 ? 4 : 2) + sizeof(int) * (size_t)B;
 }
 
 int mgr_render_forward(const void* x, const int64_t* x_strides, const float* theta, void* out, void* saved_alpha,

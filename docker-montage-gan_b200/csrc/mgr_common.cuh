@@ -30,6 +30,11 @@ struct Geometry {
   int vec8;                  // warp-specialised kernels: 16-bit footprints staged in 8-texel items (set by the launchers)
 };
 
+// layout of the forward's saved-alpha buffer: [B,L,H,W] alpha samples, padded to 256 bytes, then int flags[B]
+__host__ __device__ inline size_t saved_alpha_flags_offset(int B, int L, int H, int W, size_t elem_bytes) {
+  return (((size_t)B * L * H * W * elem_bytes) + 255) & ~(size_t)255;
+}
+
 // kVec adjacent elements -> fp32 (kVec = 4: one 16- or 8-byte load; the caller guarantees the alignment)
 template <typename T, int kVec> struct VecIO;
 template <typename T> struct VecIO<T, 1> {

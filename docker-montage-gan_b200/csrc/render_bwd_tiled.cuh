@@ -299,6 +299,16 @@ static __global__ void inverse_plans_kernel(const float* __restrict__ theta, Inv
   plans[k] = q;
 }
 
+// The forward's flags: one thread per sample, flags[b] = every layer of the sample is a pure translation.
+static __global__ void __launch_bounds__(256)
+sample_shift_flags_kernel(const float* __restrict__ theta, int B, int L, int* __restrict__ flags) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int all = 1;
+  for (int l = 0; l < L; ++l) all &= is_pure_shift(theta + ((long long)b * L + l) * 6) ? 1 : 0;
+  flags[b] = all;
+}
+
 // One CTA.  Phase 1, a thread per sample: are all of its layers pure translations?  (those samples belong to
 // render_bwd_shift).  Phase 2: the layers pass 2 has to process, in launch order (order[] minus the layers of
 // all-translation samples when the stencil kernels are on), compacted into work[0 .. wcnt[0]).  A batch of

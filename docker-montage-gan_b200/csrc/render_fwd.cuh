@@ -30,9 +30,12 @@ render_fwd_general_only(const T* __restrict__ x, const __grid_constant__ SrcLaye
 template <typename T, bool kSave>
 __global__ void __launch_bounds__(kTiledThreads, MGR_SHF_BLOCKS)
 render_fwd_stencil_only(const __grid_constant__ SrcLayers src, const float* __restrict__ theta, T* __restrict__ out,
-                        typename SavedAlpha<T>::type* __restrict__ sav, Geometry g) {
-  // every warp finds out by itself whether the sample is this kernel's (no CTA barrier before an idle CTA leaves)
-  if (!__all_sync(0xffffffffu, (int)(threadIdx.x & 31) >= g.L || is_pure_shift(theta + ((long long)blockIdx.z * g.L + (threadIdx.x & 31)) * 6))) return;
+                        typename SavedAlpha<T>::type* __restrict__ sav, Geometry g, const int* __restrict__ shift_flags) {
+  // is the sample this kernel's?  One load of the forward's per-sample flag if there is one, else every warp finds out
+  // by itself from the placements (no CTA barrier before an idle CTA leaves)
+  if (shift_flags ? shift_flags[blockIdx.z] == 0
+                  : !__all_sync(0xffffffffu, (int)(threadIdx.x & 31) >= g.L || is_pure_shift(theta + ((long long)blockIdx.z * g.L + (threadIdx.x & 31)) * 6)))
+    return;
   fwd_shift_body<T, kSave>(src, theta, out, sav, g);
 }
 

@@ -396,15 +396,16 @@ __device__ __forceinline__ void fwd_consume_tile(const T* __restrict__ x, const 
 template <typename T, bool kSave, bool kRagged>
 __global__ void __launch_bounds__(kWsThreads, MGR_WSF_BLOCKS)
 render_fwd_ws(const T* __restrict__ x, const __grid_constant__ SrcLayers src, const float* __restrict__ theta, T* __restrict__ out,
-              typename SavedAlpha<T>::type* __restrict__ sav, Geometry g, int skip_all_shift) {
+              typename SavedAlpha<T>::type* __restrict__ sav, Geometry g, int skip_all_shift, const int* __restrict__ shift_flags) {
   using Vec = typename Texel<T>::Vec;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int tid = threadIdx.x;
   const int b = blockIdx.z;
   const float* theta_b = theta + (long long)b * g.L * 6;
-  // a stack of pure translations belongs to the stencil kernel (render_fwd_stencil_only), launched next to this one;
-  // every warp finds out by itself and leaves without a CTA barrier
-  if (skip_all_shift && warp_all_shift(theta_b, g.L, tid & 31)) return;
+  // a stack of pure translations belongs to the stencil kernel (render_fwd_stencil_only), launched next to this one:
+  // one load of the per-sample flag when the forward wrote it (it does when there is a saved-alpha buffer to hold it),
+  // else every warp finds out by itself from the placements -- either way without a CTA barrier
+  if (skip_all_shift && (shift_flags ? shift_flags[b] != 0 : warp_all_shift(theta_b, g.L, tid & 31))) return;
   WsSync* sy = reinterpret_cast<WsSync*>(smem_raw);
   Vec* buf = reinterpret_cast<Vec*>(smem_raw + kWsSyncBytes);                               // [WsStages][kSlotUnits]
   LayerPlan* plan = reinterpret_cast<LayerPlan*>(smem_raw + ws_ring_bytes(sizeof(Vec)));    // [L]

@@ -71,14 +71,17 @@ const char* mgr_last_error(void);
 long long mgr_kernel_launch_count(void);
 /* Testing / A-B timing only: 0 = automatic kernel selection (default), 1 = force the general
  * direct-gather kernels even where the tiled shared-memory kernels apply, 2 = tiled kernels but
- * without the pure-translation stencil kernels.  Process-wide. */
+ * without the pure-translation stencil kernels, 3 = round 1's two-barrier tiled kernels instead of the
+ * warp-specialised ones.  Process-wide. */
 int mgr_set_debug_path(int path);
 
 /*
  * Bytes of the optional "saved alpha" buffer [B,L,H,W] the forward can fill for the backward:
  * the warped alpha sample of every (layer, pixel), fp32 for MGR_F32 tensors, fp16 otherwise.
  * (What autograd would keep alive in the reference is 13x larger: the grid, the warped layers and
- * every a_over_b intermediate.)
+ * every a_over_b intermediate.)  The buffer ends with one int per sample -- "all placements of the sample
+ * are pure translations" -- which the forward writes first, so that every CTA of the two kernels that
+ * share a batch learns with one load whether a sample is its own.
  */
 size_t mgr_saved_alpha_bytes(int B, int L, int H, int W, int dtype);
 

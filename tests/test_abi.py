@@ -79,8 +79,9 @@ def test_backward_validation_and_workspace():
     assert lib.mgr_render_backward_workspace_bytes(2, 3, 8, 8, _lib.MGR_F32, 0, 3) == 0      # composite only
     assert lib.mgr_render_backward_workspace_bytes(2, 3, 8, 8, _lib.MGR_BF16, 0, 1) == 0
     assert lib.mgr_render_backward_workspace_bytes(2, 3, 8, 8, _lib.MGR_F32, 1, 3) == 2 * 3 * 64 * 8 + 2 * 64 * 16 + 2 * 3 * (128 + 4 + 4) + 32 + 2 * 4   # records, G_P, plans + order + work list, counters, sample flags
-    assert lib.mgr_saved_alpha_bytes(2, 3, 8, 8, _lib.MGR_F32) == 2 * 3 * 64 * 4
-    assert lib.mgr_saved_alpha_bytes(2, 3, 8, 8, _lib.MGR_BF16) == 2 * 3 * 64 * 2
+    assert lib.mgr_saved_alpha_bytes(2, 3, 8, 8, _lib.MGR_F32) == 2 * 3 * 64 * 4 + 2 * 4       # alpha samples (a multiple of 256 here) + a flag per sample
+    assert lib.mgr_saved_alpha_bytes(2, 3, 8, 8, _lib.MGR_BF16) == 2 * 3 * 64 * 2 + 2 * 4
+    assert lib.mgr_saved_alpha_bytes(1, 3, 8, 8, _lib.MGR_BF16) == 512 + 4                      # 384 bytes of samples, padded to 256
     need = lib.mgr_render_backward_workspace_bytes(2, 3, 8, 8, _lib.MGR_BF16, 1, 3)
     assert need == 2 * 3 * 4 * 64 * 4                # fp32 scatter accumulator of the general path dominates
     # per-tensor query: an aligned bf16 tensor with saved alphas takes the tiled kernels (records only); without saved

@@ -7,17 +7,21 @@ leaves after one look at the placements: a few KB), and summed into the figures 
     forward               forward, general placements
     translation_fwd_bwd   forward + backward of the translation-only leg (stencil kernels)
 
-Usage: python tools/update_traffic.py gpurun_out/prof.ncu-rep c2"""
+Usage: python tools/update_traffic.py gpurun_out/prof_general.ncu-rep [gpurun_out/prof_translation.ncu-rep ...] c2"""
 import csv
 import json
 import os
 import subprocess
 import sys
 
-rep, workload = sys.argv[1], sys.argv[2]
-txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(txt.splitlines()))
-hdr, units = rows[0], rows[1]
+reps, workload = sys.argv[1:-1], sys.argv[-1]
+rep = "+".join(os.path.basename(r) for r in reps)
+rows = []
+for r_ in reps:
+    txt = subprocess.run(["ncu", "-i", r_, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rr = list(csv.reader(txt.splitlines()))
+    hdr, units = rr[0], rr[1]
+    rows += [dict(zip(hdr, r)) for r in rr[2:]]
 
 
 def to_bytes(v, u):
@@ -25,8 +29,7 @@ def to_bytes(v, u):
 
 
 per_kernel = {}
-for r in rows[2:]:
-    d = dict(zip(hdr, r))
+for d in rows:
     name = d["Kernel Name"].split("(")[0].replace("void ", "").replace("mgr::", "")
     b = sum(to_bytes(d[k], units[hdr.index(k)]) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
     per_kernel.setdefault(name, []).append(b)
@@ -48,6 +51,6 @@ data[workload] = {
     "forward": total("render_fwd_ws", "render_fwd_general_only", "render_fwd<"),
     "translation_fwd_bwd": total("render_fwd_stencil_only", "render_bwd_shift"),
     "per_kernel": avg,
-    "source": f"ncu --set full, {os.path.basename(rep)}: dram__bytes_read.sum + dram__bytes_write.sum per active launch"}
+    "source": f"ncu --set full, {rep}: dram__bytes_read.sum + dram__bytes_write.sum per active launch"}
 json.dump(data, open(path, "w"), indent=1)
 print(json.dumps(data[workload], indent=1))
