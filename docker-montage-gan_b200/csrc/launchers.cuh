@@ -11,6 +11,7 @@
 #include "pil_composite.cuh"
 #include "composite_only.cuh"
 #include "render_ws.cuh"
+#include "render_shift_tma.cuh"
 
 #include <mutex>
 #include <map>
@@ -144,7 +145,19 @@ int launch_forward_tiled(const void* x, const SrcLayers& src, const float* theta
     if (stencil) {
       MGR_CUDA(cudaGetLastError());
       count_launch();
-      if (sav) render_fwd_stencil_only<T, true><<<grid, kTiledThreads, smem_b, s>>>(src, theta, (T*)out, (SA*)sav, g, flags);
+      // canvas layout that meets TMA's alignment rules: box copies into a ring, planar stencil (render_shift_tma.cuh);
+      // ragged stacks and odd strides keep the staged stencil kernel
+      CUtensorMap xmap;
+      if (!kRagged && debug_path() != 4 && shift_tma_x_map<T>(&xmap, x, g, ShiftBox<T>::W, ShiftBox<T>::H)) {
+        const size_t smem_t = shift_tma_fwd_smem_bytes<T>(g.L);
+        dim3 gridt((g.W + kSW - 1) / kSW, (g.H + kSH - 1) / kSH, g.B);
+        auto launch_t = [&](auto kern) -> int {
+          if (int rc = ensure_dynamic_smem(kern, smem_t)) return rc;
+          kern<<<gridt, kSThreads, smem_t, s>>>(xmap, theta, (T*)out, (SA*)sav, g, flags);
+          return MGR_OK;
+        };
+        if (int rc = sav ? launch_t(render_fwd_shift_tma<T, true>) : launch_t(render_fwd_shift_tma<T, false>)) return rc;
+      } else if (sav) render_fwd_stencil_only<T, true><<<grid, kTiledThreads, smem_b, s>>>(src, theta, (T*)out, (SA*)sav, g, flags);
       else render_fwd_stencil_only<T, false><<<grid, kTiledThreads, smem_b, s>>>(src, theta, (T*)out, nullptr, g, flags);
     }
     MGR_CUDA(cudaGetLastError());

@@ -1,0 +1,337 @@
+// Stencil kernels on TMA-staged planar footprints: the production case (the reference's placement network emits pure
+// translations: fukuwarai/networks.py:246-247 through custom_utils/image_utils.py:316-335).
+//
+// Under a translation (X + fx, Y + fy) the footprint of the output tile with origin (j0, i0) is the rectangle of each
+// channel plane starting at texel (j0 + X, i0 + Y): one 5-D tensor-map box copy {W: tile + 1 + alignment slack,
+// H: tile + 1, C: 4, layer, sample} per (tile, layer), issued by one lane of a producer warp into a ring of
+// shared-memory stages.  The copy unit wants the box to start on a 16-byte boundary of the row (measured: any other
+// innermost coordinate is an illegal-instruction fault, negative and past-the-end coordinates are fine --
+// tools/micro/tma_probe.cu), so the box starts at the 16-byte boundary at or left of the footprint and a thread's
+// five texels sit at one of four offsets inside two aligned shared-memory chunks: the per-layer body is compiled for
+// each offset (CTA-uniform switch), the extraction costs nothing at run time; the consumer warps wait on the stage's mbarrier and never touch global memory for x.  What the
+// copy removes, measured on the round-2 stencil forward (ncu): the staging loop (index arithmetic, 128-bit loads held in
+// registers, byte permutes to interleave the channels, bank-conflicted shared stores) was more than half of its 89
+// warp-instructions per layer-pixel.  Out-of-range texels arrive as zeros = transparent black in the [0,1] range mode; in
+// the [-1,1] mode the padding value is -1, so tiles that touch the layer's border patch the out-of-range part of the box
+// before sampling (CTA-uniform, border tiles only) -- the lerp arithmetic then sees exactly what the staged kernels saw
+// (a run of equal taps returns that value exactly: transparent stays exactly transparent).
+//
+// A thread owns a 4-wide, 2-tall strip of pixels: three rows of five texels per channel, fetched as one 64-bit (16-bit
+// storage) or 128-bit (fp32) shared load plus one 32-bit load per row, lerped along x once per row and along y once per
+// pixel with packed fp32x2 arithmetic on pairs of horizontally adjacent pixels.
+#pragma once
+#include "render_shift.cuh"
+#include "tma.cuh"
+
+#ifndef MGR_STF_BLOCKS
+#define MGR_STF_BLOCKS 2
+#endif
+
+namespace mgr {
+
+constexpr int kSW = 64, kSH = 32;                 // output tile of the TMA stencil forward
+constexpr int kSConsumers = 256;                  // 16 x 16 strips of 4 x 2 pixels
+constexpr int kSThreads = kSConsumers + 32;       // + the producer warp
+constexpr int kSMaxStages = 4;
+
+template <typename T> struct ShiftBox {
+  static constexpr int kAlign = 16 / (int)sizeof(T);        // the box starts on a 16-byte boundary of the row
+  static constexpr int W = kSW + kAlign;                    // tile + 1 tap columns + up to kAlign - 1 columns of alignment slack
+  static constexpr int H = kSH + 1;
+  static constexpr int kPlane = W * H;                      // elements per channel plane
+  static constexpr int kBytes = kPlane * 4 * (int)sizeof(T);
+  static constexpr int kStageBytes = (kBytes + 127) & ~127; // stages start on 128-byte boundaries
+  static constexpr int kStages = sizeof(T) == 4 ? 3 : 4;
+};
+
+// the taps of the tile (columns x0 .. x0 + kSW, rows y0 .. y0 + kSH) all miss the image: the layer is transparent here
+__device__ __forceinline__ bool shift_box_misses(int x0, int y0, int W, int H) {
+  return x0 + kSW < 0 || x0 >= W || y0 + kSH < 0 || y0 >= H;
+}
+
+// ---- five adjacent texels e0..e4 of one channel row -> the x-lerped values of the strip's four pixels ------------------
+// `p` points at the aligned chunk (four elements: 8 bytes of 16-bit storage, 16 bytes of fp32) that holds e0 at element
+// offset R in 0..3; e0..e4 lie inside that chunk and the next one.
+// Packed arithmetic wants its operands in aligned register pairs.  16-bit storage: every element is produced by its own
+// unpack instruction, which can write any register, so the pixels are paired (0, 2) and (1, 3): the left / right taps are
+// then the three pairs (e0, e2), (e1, e3), (e2, e4) -- seven unpacks per row, no register moves (pairing (0, 1), (2, 3)
+// needs (e0,e1), (e1,e2), (e2,e3), (e3,e4): the compiler materialised them with 9-10 moves per row).  fp32 storage: the
+// pixels are paired (0, 1) and (2, 3) (the 128-bit loads leave neighbours in neighbouring registers).
+// Pair order of the results: Row5<T>::kStrided ? {(px0, px2), (px1, px3)} : {(px0, px1), (px2, px3)}.
+template <typename T> struct Row5;
+template <> struct Row5<float> {
+  static constexpr bool kStrided = false;
+  template <int R>
+  static __device__ __forceinline__ void lerp_x(const float* p, f32x2 fx2, f32x2& h0, f32x2& h1) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    const f32x2 A0 = pk(v[R], v[R + 1]), A1 = pk(v[R + 2], v[R + 3]);
+    h0 = fma2(fx2, sub2(pk(v[R + 1], v[R + 2]), A0), A0);
+    h1 = fma2(fx2, sub2(pk(v[R + 3], v[R + 4]), A1), A1);
+  }
+};
+template <> struct Row5<__nv_bfloat16> {
+  static constexpr bool kStrided = true;
+  template <int M> static __device__ __forceinline__ float elem(const uint32_t (&w)[4]) {
+    return __uint_as_float((M & 1) ? (w[M >> 1] & 0xffff0000u) : (w[M >> 1] << 16));
+  }
+  template <int R>
+  static __device__ __forceinline__ void lerp_x(const __nv_bfloat16* p, f32x2 fx2, f32x2& h0, f32x2& h1) {
+    const uint2 c0 = *reinterpret_cast<const uint2*>(p), c1 = *reinterpret_cast<const uint2*>(p + 4);
+    const uint32_t w[4] = {c0.x, c0.y, c1.x, c1.y};
+    const f32x2 P02 = pk(elem<R>(w), elem<R + 2>(w));
+    const f32x2 P13 = pk(elem<R + 1>(w), elem<R + 3>(w));
+    const f32x2 P24 = pk(elem<R + 2>(w), elem<R + 4>(w));
+    h0 = fma2(fx2, sub2(P13, P02), P02);
+    h1 = fma2(fx2, sub2(P24, P13), P13);
+  }
+};
+template <> struct Row5<__half> {
+  static constexpr bool kStrided = true;
+  template <int M> static __device__ __forceinline__ float elem(const uint32_t (&w)[4]) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&w[M >> 1]);
+    return (M & 1) ? __high2float(h) : __low2float(h);
+  }
+  template <int R>
+  static __device__ __forceinline__ void lerp_x(const __half* p, f32x2 fx2, f32x2& h0, f32x2& h1) {
+    const uint2 c0 = *reinterpret_cast<const uint2*>(p), c1 = *reinterpret_cast<const uint2*>(p + 4);
+    const uint32_t w[4] = {c0.x, c0.y, c1.x, c1.y};
+    const f32x2 P02 = pk(elem<R>(w), elem<R + 2>(w));
+    const f32x2 P13 = pk(elem<R + 1>(w), elem<R + 3>(w));
+    const f32x2 P24 = pk(elem<R + 2>(w), elem<R + 4>(w));
+    h0 = fma2(fx2, sub2(P13, P02), P02);
+    h1 = fma2(fx2, sub2(P24, P13), P13);
+  }
+};
+// two packed pairs -> the four pixels in column order
+template <typename T>
+__device__ __forceinline__ void strip_unpack(f32x2 q0, f32x2 q1, float (&v)[4]) {
+  if (Row5<T>::kStrided) { upk(q0, v[0], v[2]); upk(q1, v[1], v[3]); }
+  else { upk(q0, v[0], v[1]); upk(q1, v[2], v[3]); }
+}
+
+template <typename T> __device__ __forceinline__ T raw_minus_one();
+template <> __device__ __forceinline__ float raw_minus_one<float>() { return -1.f; }
+template <> __device__ __forceinline__ __nv_bfloat16 raw_minus_one<__nv_bfloat16>() { return __ushort_as_bfloat16((unsigned short)0xBF80u); }
+template <> __device__ __forceinline__ __half raw_minus_one<__half>() { return __ushort_as_half((unsigned short)0xBC00u); }
+
+// [-1,1] range mode: texels of the box outside the image become the padding value -1 (the copy zero-fills them).
+// Threads 0..255 of the consumer group.
+template <typename T>
+__device__ __forceinline__ void shift_patch_oob(T* stage, int x0, int y0, int W, int H, int tid) {   // (x0, y0): texel of box element (0, 0)
+  constexpr int BW = ShiftBox<T>::W, BH = ShiftBox<T>::H, NC = ShiftBox<T>::W;
+  const int nT = min(max(-y0, 0), BH), nB = min(max(y0 + BH - H, 0), BH);
+  const int nL = min(max(-x0, 0), NC), nR = min(max(x0 + NC - W, 0), NC);
+  const T m1 = raw_minus_one<T>();
+  const int cl = tid & 7, rl = tid >> 3;                    // 8 column lanes x 32 row lanes
+  for (int r = rl; r < BH; r += 32) {
+    const bool row_out = r < nT || r >= BH - nB;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      T* row = stage + c * ShiftBox<T>::kPlane + r * BW;
+      if (row_out) {
+        for (int k = cl; k < NC; k += 8) row[k] = m1;
+      } else {
+        for (int k = cl; k < nL; k += 8) row[k] = m1;
+        for (int k = NC - nR + cl; k < NC; k += 8) row[k] = m1;
+      }
+    }
+  }
+}
+
+template <typename SA> __device__ __forceinline__ void st_alpha4(SA* p, float a0, float a1, float a2, float a3);
+template <> __device__ __forceinline__ void st_alpha4<float>(float* p, float a0, float a1, float a2, float a3) {
+  *reinterpret_cast<float4*>(p) = make_float4(a0, a1, a2, a3);
+}
+template <> __device__ __forceinline__ void st_alpha4<__half>(__half* p, float a0, float a1, float a2, float a3) {
+  const __half2 lo_ = __floats2half2_rn(a0, a1), hi_ = __floats2half2_rn(a2, a3);
+  uint2 t;
+  t.x = *reinterpret_cast<const uint32_t*>(&lo_); t.y = *reinterpret_cast<const uint32_t*>(&hi_);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+
+// One channel of a 4 x 2 strip: raw bilinear samples of two rows of two pixel pairs (lerp form, x then y).
+template <typename T, int R>
+__device__ __forceinline__ void shift_sample_strip(const T* p, f32x2 fx2, f32x2 fy2, f32x2 (&v)[2][2]) {
+  constexpr int BW = ShiftBox<T>::W;
+  f32x2 h0[3], h1[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    Row5<T>::template lerp_x<R>(p + r * BW, fx2, h0[r], h1[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    v[r][0] = fma2(fy2, sub2(h0[r + 1], h0[r]), h0[r]);
+    v[r][1] = fma2(fy2, sub2(h1[r + 1], h1[r]), h1[r]);
+  }
+}
+
+struct ShiftRing {
+  uint64_t full[kSMaxStages];       // the copy's bytes have landed (tx count), consumers wait
+  uint64_t empty[kSMaxStages];      // one arrival per consumer warp, the producer waits
+};
+
+template <typename T>
+inline size_t shift_tma_fwd_smem_bytes(int L) {
+  return (size_t)ShiftBox<T>::kStageBytes * ShiftBox<T>::kStages + sizeof(ShiftPlan) * (size_t)L + sizeof(ShiftRing);
+}
+
+template <typename T, bool kSave>
+__global__ void __launch_bounds__(kSThreads, sizeof(T) == 4 ? 2 : MGR_STF_BLOCKS)
+render_fwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ theta, T* __restrict__ out,
+                     typename SavedAlpha<T>::type* __restrict__ sav, Geometry g, const int* __restrict__ shift_flags) {
+  using SA = typename SavedAlpha<T>::type;
+  using Box = ShiftBox<T>;
+  constexpr int S = Box::kStages;
+  const int b = blockIdx.z;
+  // is the sample this kernel's?  (flag written by sample_shift_flags_kernel; without one every warp looks at the placements)
+  if (shift_flags ? shift_flags[b] == 0
+                  : !__all_sync(0xffffffffu, (int)(threadIdx.x & 31) >= g.L || is_pure_shift(theta + ((long long)b * g.L + (threadIdx.x & 31)) * 6)))
+    return;
+  extern __shared__ __align__(128) unsigned char smem[];     // no static shared memory in this kernel: the window starts aligned
+  ShiftPlan* splan = reinterpret_cast<ShiftPlan*>(smem + (size_t)Box::kStageBytes * S);
+  ShiftRing* ring = reinterpret_cast<ShiftRing*>(splan + g.L);
+  const int tid = threadIdx.x;
+  const int j0 = blockIdx.x * kSW, i0 = blockIdx.y * kSH;
+  for (int l = tid; l < g.L; l += kSThreads) splan[l] = make_shift_plan(theta + ((long long)b * g.L + l) * 6, g.H, g.W);
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) { tma_mbar_init(&ring->full[s], 1); tma_mbar_init(&ring->empty[s], kSConsumers / 32); }
+    tma_fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (tid >= kSConsumers) {                       // ---- producer warp: one lane issues the box copies ----
+    if (tid == kSConsumers) {
+      tma_prefetch_map(&xmap);
+      int it = 0;
+      for (int l = 0; l < g.L; ++l) {
+        const int x0 = j0 + splan[l].X, y0 = i0 + splan[l].Y;
+        if (shift_box_misses(x0, y0, g.W, g.H)) continue;
+        const int s = it % S;
+        if (it >= S) tma_mbar_wait(&ring->empty[s], (uint32_t)((it / S) - 1) & 1u);
+        tma_mbar_expect_tx(&ring->full[s], (uint32_t)Box::kBytes);
+        tma_load_5d(smem + (size_t)Box::kStageBytes * s, &xmap, &ring->full[s], x0 & ~(Box::kAlign - 1), y0, 0, l, b);
+        ++it;
+      }
+    }
+    return;
+  }
+
+  // ---- consumers ----
+  const int tx = tid & 15, ty = tid >> 4;
+  const int j = j0 + 4 * tx, i = i0 + 2 * ty;
+  const bool col_live = j < g.W;                            // W is a multiple of 4: a strip is inside or outside as a whole
+  const bool live0 = col_live && i < g.H, live1 = col_live && i + 1 < g.H;
+  const int hw = g.H * g.W;
+  const f32x2 zs2 = bc(g.m11 ? 0.5f : 1.f), zb2 = bc(g.m11 ? 0.5f : 0.f), one2 = bc(1.f);
+  f32x2 Sc[3][2][2], R_[2][2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int p = 0; p < 2; ++p) { Sc[0][r][p] = Sc[1][r][p] = Sc[2][r][p] = R_[r][p] = bc(0.f); }
+  const int toff = (2 * ty) * Box::W + 4 * tx;              // this strip's aligned chunk inside a plane of the box, before the layer's offset
+  const int poff = i * g.W + j;                               // this strip's first pixel inside a plane (H * W < 2^29)
+
+  int it = 0;
+  for (int l = 0; l < g.L; ++l) {
+    const ShiftPlan sp = splan[l];
+    const int x0 = j0 + sp.X, y0 = i0 + sp.Y;
+    SA* sv = kSave ? sav + ((long long)b * g.L + l) * hw + poff : nullptr;      // CTA-uniform base + one 32-bit offset
+    if (shift_box_misses(x0, y0, g.W, g.H)) {
+      if (kSave) {
+        if (live0) st_alpha4<SA>(sv, 0.f, 0.f, 0.f, 0.f);
+        if (live1) st_alpha4<SA>(sv + g.W, 0.f, 0.f, 0.f, 0.f);
+      }
+      continue;
+    }
+    const int s = it % S;
+    T* stage = reinterpret_cast<T*>(smem + (size_t)Box::kStageBytes * s);
+    const int xa = x0 & ~(Box::kAlign - 1), dx = x0 - xa;     // box origin and the footprint's offset inside it
+    tma_mbar_wait(&ring->full[s], (uint32_t)(it / S) & 1u);
+    if (g.m11 && (xa < 0 || xa + Box::W > g.W || y0 < 0 || y0 + Box::H > g.H)) {       // CTA-uniform
+      shift_patch_oob<T>(stage, xa, y0, g.W, g.H, tid);
+      tma_fence_proxy_async();
+      named_barrier(1, kSConsumers);
+    }
+    const f32x2 fx2 = bc(sp.fx), fy2 = bc(sp.fy);
+    const T* p = stage + toff + (dx & ~3);
+    // the layer body, compiled once per element offset R = dx & 3 of e0 inside its aligned chunk
+    auto body = [&](auto rtag) {
+      constexpr int R = decltype(rtag)::value;
+      f32x2 a[2][2], om[2][2];
+      {
+        f32x2 v[2][2];
+        shift_sample_strip<T, R>(p + 3 * Box::kPlane, fx2, fy2, v);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            a[r][q] = fma2(v[r][q], zs2, zb2);
+            om[r][q] = sub2(one2, a[r][q]);
+            R_[r][q] = fma2(om[r][q], R_[r][q], a[r][q]);
+          }
+      }
+      if (kSave) {
+        float av[4];
+        strip_unpack<T>(a[0][0], a[0][1], av);
+        if (live0) st_alpha4<SA>(sv, av[0], av[1], av[2], av[3]);
+        strip_unpack<T>(a[1][0], a[1][1], av);
+        if (live1) st_alpha4<SA>(sv + g.W, av[0], av[1], av[2], av[3]);
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        f32x2 v[2][2];
+        shift_sample_strip<T, R>(p + c * Box::kPlane, fx2, fy2, v);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) Sc[c][r][q] = fma2(om[r][q], Sc[c][r][q], mul2(a[r][q], fma2(v[r][q], zs2, zb2)));
+      }
+    };
+    switch (dx & 3) {
+      case 0: body(std::integral_constant<int, 0>{}); break;
+      case 1: body(std::integral_constant<int, 1>{}); break;
+      case 2: body(std::integral_constant<int, 2>{}); break;
+      default: body(std::integral_constant<int, 3>{}); break;
+    }
+    __syncwarp();
+    if ((tid & 31) == 0) tma_mbar_arrive(&ring->empty[s]);
+    ++it;
+  }
+
+  const float os = g.m11 ? 2.f : 1.f, obias = g.m11 ? -1.f : 0.f;
+  T* outp = out + (long long)b * 4 * hw + poff;
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    if (!(r ? live1 : live0)) continue;
+    float Rv[4], inv[4];
+    strip_unpack<T>(R_[r][0], R_[r][1], Rv);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) inv[k] = (Rv[k] != 0.f) ? 1.f / Rv[k] : 0.f;       // nan_to_num(0/0) = 0 (image_utils.py:132)
+    T* o = outp + r * g.W;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      float sv4[4], ov[4];
+      strip_unpack<T>(Sc[c][r][0], Sc[c][r][1], sv4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) ov[k] = fmaf(sv4[k] * inv[k], os, obias);
+      st_vec4<T>(o + c * hw, ov);
+    }
+    float av[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) av[k] = fmaf(Rv[k], os, obias);
+    st_vec4<T>(o + 3 * hw, av);
+  }
+}
+
+// the 5-D map {W, H, 4, L, B} over the canvas layout x[B,L,4,H,W] with the forward's box; false: keep the staged kernel
+template <typename T>
+inline bool shift_tma_x_map(CUtensorMap* map, const void* x, const Geometry& g, int box_w, int box_h) {
+  const long long dims[5] = {g.W, g.H, 4, g.L, g.B};
+  const long long strides[5] = {1, g.sh, g.sc, g.sl, g.sb};
+  const int box[5] = {box_w, box_h, 4, 1, 1};
+  return tma_make_map(map, x, (int)sizeof(T), 5, dims, strides, box);
+}
+
+}  // namespace mgr
