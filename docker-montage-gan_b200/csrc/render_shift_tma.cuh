@@ -62,52 +62,58 @@ template <typename T> struct Row5;
 template <> struct Row5<float> {
   static constexpr bool kStrided = false;
   template <int R>
-  static __device__ __forceinline__ void lerp_x(const float* p, f32x2 fx2, f32x2& h0, f32x2& h1) {
+  static __device__ __forceinline__ void taps(const float* p, int, f32x2& L0, f32x2& L1, f32x2& R0, f32x2& R1) {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    const f32x2 A0 = pk(v[R], v[R + 1]), A1 = pk(v[R + 2], v[R + 3]);
-    h0 = fma2(fx2, sub2(pk(v[R + 1], v[R + 2]), A0), A0);
-    h1 = fma2(fx2, sub2(pk(v[R + 3], v[R + 4]), A1), A1);
+    L0 = pk(v[R], v[R + 1]); L1 = pk(v[R + 2], v[R + 3]);
+    R0 = pk(v[R + 1], v[R + 2]); R1 = pk(v[R + 3], v[R + 4]);
   }
 };
+// 16-bit storage: `p` points at the EVEN element at or left of e0 (a 32-bit word boundary), `sh` = 16 if e0 is the odd half
+// of that word, else 0.  Three 32-bit loads and three funnel shifts give the words (e0,e1), (e2,e3), (e4,.) whatever the
+// alignment, so ONE copy of the layer body serves every offset (four copies, one per offset inside an aligned 8-byte chunk,
+// put the backward's layer loop at 44 KB of code: ncu showed 32 % of the stall samples waiting for instructions).
+struct Words3 { uint32_t a0, a1, a2; };
+template <typename T>
+__device__ __forceinline__ Words3 row_words(const T* p, int sh) {
+  const uint32_t* q = reinterpret_cast<const uint32_t*>(p);
+  const uint32_t w0 = q[0], w1 = q[1], w2 = q[2];
+  Words3 r;
+  r.a0 = __funnelshift_r(w0, w1, sh); r.a1 = __funnelshift_r(w1, w2, sh); r.a2 = w2 >> sh;
+  return r;
+}
 template <> struct Row5<__nv_bfloat16> {
   static constexpr bool kStrided = true;
-  template <int M> static __device__ __forceinline__ float elem(const uint32_t (&w)[4]) {
-    return __uint_as_float((M & 1) ? (w[M >> 1] & 0xffff0000u) : (w[M >> 1] << 16));
-  }
   template <int R>
-  static __device__ __forceinline__ void lerp_x(const __nv_bfloat16* p, f32x2 fx2, f32x2& h0, f32x2& h1) {
-    const uint2 c0 = *reinterpret_cast<const uint2*>(p), c1 = *reinterpret_cast<const uint2*>(p + 4);
-    const uint32_t w[4] = {c0.x, c0.y, c1.x, c1.y};
-    const f32x2 P02 = pk(elem<R>(w), elem<R + 2>(w));
-    const f32x2 P13 = pk(elem<R + 1>(w), elem<R + 3>(w));
-    const f32x2 P24 = pk(elem<R + 2>(w), elem<R + 4>(w));
-    h0 = fma2(fx2, sub2(P13, P02), P02);
-    h1 = fma2(fx2, sub2(P24, P13), P13);
+  static __device__ __forceinline__ void taps(const __nv_bfloat16* p, int sh, f32x2& L0, f32x2& L1, f32x2& R0, f32x2& R1) {
+    const Words3 w = row_words(p, sh);
+    L0 = pk(__uint_as_float(w.a0 << 16), __uint_as_float(w.a1 << 16));
+    L1 = R0 = pk(__uint_as_float(w.a0 & 0xffff0000u), __uint_as_float(w.a1 & 0xffff0000u));
+    R1 = pk(__uint_as_float(w.a1 << 16), __uint_as_float(w.a2 << 16));
   }
 };
 template <> struct Row5<__half> {
   static constexpr bool kStrided = true;
-  template <int M> static __device__ __forceinline__ float elem(const uint32_t (&w)[4]) {
-    const __half2 h = *reinterpret_cast<const __half2*>(&w[M >> 1]);
-    return (M & 1) ? __high2float(h) : __low2float(h);
-  }
   template <int R>
-  static __device__ __forceinline__ void lerp_x(const __half* p, f32x2 fx2, f32x2& h0, f32x2& h1) {
-    const uint2 c0 = *reinterpret_cast<const uint2*>(p), c1 = *reinterpret_cast<const uint2*>(p + 4);
-    const uint32_t w[4] = {c0.x, c0.y, c1.x, c1.y};
-    const f32x2 P02 = pk(elem<R>(w), elem<R + 2>(w));
-    const f32x2 P13 = pk(elem<R + 1>(w), elem<R + 3>(w));
-    const f32x2 P24 = pk(elem<R + 2>(w), elem<R + 4>(w));
-    h0 = fma2(fx2, sub2(P13, P02), P02);
-    h1 = fma2(fx2, sub2(P24, P13), P13);
+  static __device__ __forceinline__ void taps(const __half* p, int sh, f32x2& L0, f32x2& L1, f32x2& R0, f32x2& R1) {
+    const Words3 w = row_words(p, sh);
+    const __half2 h0 = *reinterpret_cast<const __half2*>(&w.a0), h1 = *reinterpret_cast<const __half2*>(&w.a1),
+                  h2 = *reinterpret_cast<const __half2*>(&w.a2);
+    L0 = pk(__low2float(h0), __low2float(h1));
+    L1 = R0 = pk(__high2float(h0), __high2float(h1));
+    R1 = pk(__low2float(h1), __low2float(h2));
   }
 };
-// two packed pairs -> the four pixels in column order
+// two packed pairs <-> the four pixels in column order
 template <typename T>
 __device__ __forceinline__ void strip_unpack(f32x2 q0, f32x2 q1, float (&v)[4]) {
   if (Row5<T>::kStrided) { upk(q0, v[0], v[2]); upk(q1, v[1], v[3]); }
   else { upk(q0, v[0], v[1]); upk(q1, v[2], v[3]); }
+}
+template <typename T>
+__device__ __forceinline__ void strip_pack(const float (&v)[4], f32x2& q0, f32x2& q1) {
+  if (Row5<T>::kStrided) { q0 = pk(v[0], v[2]); q1 = pk(v[1], v[3]); }
+  else { q0 = pk(v[0], v[1]); q1 = pk(v[2], v[3]); }
 }
 
 template <typename T> __device__ __forceinline__ T raw_minus_one();
@@ -123,18 +129,19 @@ __device__ __forceinline__ void shift_patch_oob(T* stage, int x0, int y0, int W,
   const int nT = min(max(-y0, 0), BH), nB = min(max(y0 + BH - H, 0), BH);
   const int nL = min(max(-x0, 0), NC), nR = min(max(x0 + NC - W, 0), NC);
   const T m1 = raw_minus_one<T>();
-  const int cl = tid & 7, rl = tid >> 3;                    // 8 column lanes x 32 row lanes
-  for (int r = rl; r < BH; r += 32) {
-    const bool row_out = r < nT || r >= BH - nB;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      T* row = stage + c * ShiftBox<T>::kPlane + r * BW;
-      if (row_out) {
-        for (int k = cl; k < NC; k += 8) row[k] = m1;
-      } else {
-        for (int k = cl; k < nL; k += 8) row[k] = m1;
-        for (int k = NC - nR + cl; k < NC; k += 8) row[k] = m1;
-      }
+  const int cl = tid & 7;                                     // 8 column lanes x 32 (row, channel) lanes
+#pragma unroll 1
+  for (int rc = tid >> 3; rc < 4 * BH; rc += kSConsumers / 8) {
+    const int r = rc >> 2, c = rc & 3;
+    T* row = stage + c * ShiftBox<T>::kPlane + r * BW;
+    if (r < nT || r >= BH - nB) {
+#pragma unroll 1
+      for (int k = cl; k < NC; k += 8) row[k] = m1;
+    } else {
+#pragma unroll 1
+      for (int k = cl; k < nL; k += 8) row[k] = m1;
+#pragma unroll 1
+      for (int k = NC - nR + cl; k < NC; k += 8) row[k] = m1;
     }
   }
 }
@@ -152,12 +159,15 @@ template <> __device__ __forceinline__ void st_alpha4<__half>(__half* p, float a
 
 // One channel of a 4 x 2 strip: raw bilinear samples of two rows of two pixel pairs (lerp form, x then y).
 template <typename T, int R>
-__device__ __forceinline__ void shift_sample_strip(const T* p, f32x2 fx2, f32x2 fy2, f32x2 (&v)[2][2]) {
+__device__ __forceinline__ void shift_sample_strip(const T* p, int sh, f32x2 fx2, f32x2 fy2, f32x2 (&v)[2][2]) {
   constexpr int BW = ShiftBox<T>::W;
   f32x2 h0[3], h1[3];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    Row5<T>::template lerp_x<R>(p + r * BW, fx2, h0[r], h1[r]);
+    f32x2 L0, L1, R0, R1;
+    Row5<T>::template taps<R>(p + r * BW, sh, L0, L1, R0, R1);
+    h0[r] = fma2(fx2, sub2(R0, L0), L0);
+    h1[r] = fma2(fx2, sub2(R1, L1), L1);
   }
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
@@ -255,14 +265,16 @@ render_fwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const float* __re
       named_barrier(1, kSConsumers);
     }
     const f32x2 fx2 = bc(sp.fx), fy2 = bc(sp.fy);
-    const T* p = stage + toff + (dx & ~3);
-    // the layer body, compiled once per element offset R = dx & 3 of e0 inside its aligned chunk
+    // fp32: e0 sits at offset R = dx in 0..3 of the strip's aligned 16-byte chunk, the body is compiled per R;
+    // 16-bit: one body, the row words are funnel-shifted into place (Row5)
+    const T* p = stage + toff + (sizeof(T) == 2 ? (dx & ~1) : 0);
+    const int sh = (dx & 1) * 16;
     auto body = [&](auto rtag) {
       constexpr int R = decltype(rtag)::value;
       f32x2 a[2][2], om[2][2];
       {
         f32x2 v[2][2];
-        shift_sample_strip<T, R>(p + 3 * Box::kPlane, fx2, fy2, v);
+        shift_sample_strip<T, R>(p + 3 * Box::kPlane, sh, fx2, fy2, v);
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
@@ -282,14 +294,15 @@ render_fwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const float* __re
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
         f32x2 v[2][2];
-        shift_sample_strip<T, R>(p + c * Box::kPlane, fx2, fy2, v);
+        shift_sample_strip<T, R>(p + c * Box::kPlane, sh, fx2, fy2, v);
 #pragma unroll
         for (int r = 0; r < 2; ++r)
 #pragma unroll
           for (int q = 0; q < 2; ++q) Sc[c][r][q] = fma2(om[r][q], Sc[c][r][q], mul2(a[r][q], fma2(v[r][q], zs2, zb2)));
       }
     };
-    switch (dx & 3) {
+    if constexpr (sizeof(T) == 2) body(std::integral_constant<int, 0>{});
+    else switch (dx & 3) {
       case 0: body(std::integral_constant<int, 0>{}); break;
       case 1: body(std::integral_constant<int, 1>{}); break;
       case 2: body(std::integral_constant<int, 2>{}); break;

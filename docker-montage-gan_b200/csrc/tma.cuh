@@ -83,11 +83,11 @@ __device__ __forceinline__ void tma_mbar_wait(uint64_t* bar, uint32_t parity) {
       "{\n"
       ".reg .pred P1;\n"
       "TMA_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"      // suspends up to the hint, wakes when the phase completes
       "@P1 bra TMA_DONE;\n"
       "bra TMA_WAIT;\n"
       "TMA_DONE:\n"
-      "}" ::"r"(tma_smem_u32(bar)), "r"(parity) : "memory");
+      "}" ::"r"(tma_smem_u32(bar)), "r"(parity), "r"(0x989680u) : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_map(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
