@@ -23,6 +23,9 @@
 #include "render_shift.cuh"
 #include "tma.cuh"
 
+#ifndef MGR_STF_STAGES16
+#define MGR_STF_STAGES16 4
+#endif
 #ifndef MGR_STF_BLOCKS
 #define MGR_STF_BLOCKS 2
 #endif
@@ -41,7 +44,7 @@ template <typename T> struct ShiftBox {
   static constexpr int kPlane = W * H;                      // elements per channel plane
   static constexpr int kBytes = kPlane * 4 * (int)sizeof(T);
   static constexpr int kStageBytes = (kBytes + 127) & ~127; // stages start on 128-byte boundaries
-  static constexpr int kStages = sizeof(T) == 4 ? 3 : 4;
+  static constexpr int kStages = sizeof(T) == 4 ? 3 : MGR_STF_STAGES16;
 };
 
 // the taps of the tile (columns x0 .. x0 + kSW, rows y0 .. y0 + kSH) all miss the image: the layer is transparent here
@@ -82,26 +85,53 @@ __device__ __forceinline__ Words3 row_words(const T* p, int sh) {
   r.a0 = __funnelshift_r(w0, w1, sh); r.a1 = __funnelshift_r(w1, w2, sh); r.a2 = w2 >> sh;
   return r;
 }
+// R = -1: funnel-shifted words (p = even element, runtime sh); R = 0..3: e0 at compile-time offset R of the aligned 8-byte
+// chunk at p (two 64-bit loads, no shifts: what the forward uses -- its four bodies fit the instruction cache)
 template <> struct Row5<__nv_bfloat16> {
   static constexpr bool kStrided = true;
+  template <int M> static __device__ __forceinline__ float elem(const uint32_t (&w)[4]) {
+    return __uint_as_float((M & 1) ? (w[M >> 1] & 0xffff0000u) : (w[M >> 1] << 16));
+  }
   template <int R>
   static __device__ __forceinline__ void taps(const __nv_bfloat16* p, int sh, f32x2& L0, f32x2& L1, f32x2& R0, f32x2& R1) {
-    const Words3 w = row_words(p, sh);
-    L0 = pk(__uint_as_float(w.a0 << 16), __uint_as_float(w.a1 << 16));
-    L1 = R0 = pk(__uint_as_float(w.a0 & 0xffff0000u), __uint_as_float(w.a1 & 0xffff0000u));
-    R1 = pk(__uint_as_float(w.a1 << 16), __uint_as_float(w.a2 << 16));
+    if constexpr (R < 0) {
+      const Words3 w = row_words(p, sh);
+      L0 = pk(__uint_as_float(w.a0 << 16), __uint_as_float(w.a1 << 16));
+      L1 = R0 = pk(__uint_as_float(w.a0 & 0xffff0000u), __uint_as_float(w.a1 & 0xffff0000u));
+      R1 = pk(__uint_as_float(w.a1 << 16), __uint_as_float(w.a2 << 16));
+    } else {
+      const uint2 c0 = *reinterpret_cast<const uint2*>(p), c1 = *reinterpret_cast<const uint2*>(p + 4);
+      const uint32_t w[4] = {c0.x, c0.y, c1.x, c1.y};
+      constexpr int Q = R < 0 ? 0 : R;
+      L0 = pk(elem<Q>(w), elem<Q + 2>(w));
+      L1 = R0 = pk(elem<Q + 1>(w), elem<Q + 3>(w));
+      R1 = pk(elem<Q + 2>(w), elem<Q + 4>(w));
+    }
   }
 };
 template <> struct Row5<__half> {
   static constexpr bool kStrided = true;
+  template <int M> static __device__ __forceinline__ float elem(const uint32_t (&w)[4]) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&w[M >> 1]);
+    return (M & 1) ? __high2float(h) : __low2float(h);
+  }
   template <int R>
   static __device__ __forceinline__ void taps(const __half* p, int sh, f32x2& L0, f32x2& L1, f32x2& R0, f32x2& R1) {
-    const Words3 w = row_words(p, sh);
-    const __half2 h0 = *reinterpret_cast<const __half2*>(&w.a0), h1 = *reinterpret_cast<const __half2*>(&w.a1),
-                  h2 = *reinterpret_cast<const __half2*>(&w.a2);
-    L0 = pk(__low2float(h0), __low2float(h1));
-    L1 = R0 = pk(__high2float(h0), __high2float(h1));
-    R1 = pk(__low2float(h1), __low2float(h2));
+    if constexpr (R < 0) {
+      const Words3 w = row_words(p, sh);
+      const __half2 h0 = *reinterpret_cast<const __half2*>(&w.a0), h1 = *reinterpret_cast<const __half2*>(&w.a1),
+                    h2 = *reinterpret_cast<const __half2*>(&w.a2);
+      L0 = pk(__low2float(h0), __low2float(h1));
+      L1 = R0 = pk(__high2float(h0), __high2float(h1));
+      R1 = pk(__low2float(h1), __low2float(h2));
+    } else {
+      const uint2 c0 = *reinterpret_cast<const uint2*>(p), c1 = *reinterpret_cast<const uint2*>(p + 4);
+      const uint32_t w[4] = {c0.x, c0.y, c1.x, c1.y};
+      constexpr int Q = R < 0 ? 0 : R;
+      L0 = pk(elem<Q>(w), elem<Q + 2>(w));
+      L1 = R0 = pk(elem<Q + 1>(w), elem<Q + 3>(w));
+      R1 = pk(elem<Q + 2>(w), elem<Q + 4>(w));
+    }
   }
 };
 // two packed pairs <-> the four pixels in column order
@@ -265,10 +295,9 @@ render_fwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const float* __re
       named_barrier(1, kSConsumers);
     }
     const f32x2 fx2 = bc(sp.fx), fy2 = bc(sp.fy);
-    // fp32: e0 sits at offset R = dx in 0..3 of the strip's aligned 16-byte chunk, the body is compiled per R;
-    // 16-bit: one body, the row words are funnel-shifted into place (Row5)
-    const T* p = stage + toff + (sizeof(T) == 2 ? (dx & ~1) : 0);
-    const int sh = (dx & 1) * 16;
+    // e0 sits at offset R = dx & 3 of the strip's aligned chunk (8 bytes of 16-bit storage, 16 of fp32): the body is compiled per R
+    const T* p = stage + toff + (dx & ~3);
+    const int sh = 0;
     auto body = [&](auto rtag) {
       constexpr int R = decltype(rtag)::value;
       f32x2 a[2][2], om[2][2];
@@ -301,8 +330,7 @@ render_fwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const float* __re
           for (int q = 0; q < 2; ++q) Sc[c][r][q] = fma2(om[r][q], Sc[c][r][q], mul2(a[r][q], fma2(v[r][q], zs2, zb2)));
       }
     };
-    if constexpr (sizeof(T) == 2) body(std::integral_constant<int, 0>{});
-    else switch (dx & 3) {
+    switch (dx & 3) {
       case 0: body(std::integral_constant<int, 0>{}); break;
       case 1: body(std::integral_constant<int, 1>{}); break;
       case 2: body(std::integral_constant<int, 2>{}); break;

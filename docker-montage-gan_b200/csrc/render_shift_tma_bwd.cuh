@@ -21,6 +21,9 @@
 #pragma once
 #include "render_shift_tma.cuh"
 
+#ifndef MGR_STB_STAGES
+#define MGR_STB_STAGES 2
+#endif
 #ifndef MGR_STB_BLOCKS
 #define MGR_STB_BLOCKS 3
 #endif
@@ -31,7 +34,7 @@ constexpr int kBW = 64, kBH = 16;                 // pixel tile
 constexpr int kBAncW = kBW - 1, kBAncH = kBH - 1; // anchors a CTA owns
 constexpr int kBConsumers = 128;                  // 16 x 8 strips of 4 x 2 pixels
 constexpr int kBThreads = kBConsumers + 32;
-constexpr int kBStages = 2;
+constexpr int kBStages = MGR_STB_STAGES;
 
 template <typename T> struct BwdBox {
   using SA = typename SavedAlpha<T>::type;
@@ -426,7 +429,7 @@ render_bwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const __grid_cons
         th6[5] = sy0 + sy1;
       }
     };
-    if constexpr (sizeof(T) == 2) body(std::integral_constant<int, 0>{});
+    if constexpr (sizeof(T) == 2) body(std::integral_constant<int, -1>{});
     else switch (dx0 & 3) {
       case 0: body(std::integral_constant<int, 0>{}); break;
       case 1: body(std::integral_constant<int, 1>{}); break;
