@@ -14,6 +14,7 @@
 #include "render_shift_tma.cuh"
 #include "render_shift_tma_bwd.cuh"
 
+#include <cstdlib>
 #include <mutex>
 #include <map>
 #include <utility>
@@ -100,6 +101,33 @@ const char* ragged_problem(const SrcLayers& src, const DstLayers* dst, const Geo
   return nullptr;
 }
 
+// fork the general kernels onto the side stream?  Only where an idle launch costs more than the fork / join (four runtime
+// calls): from about a million layer-pixels; MGR_NO_SIDE_STREAM=1 in the environment keeps everything on one stream
+inline bool use_side_stream(const Geometry& g) {
+  static const bool off = [] { const char* e = getenv("MGR_NO_SIDE_STREAM"); return e && e[0] == '1'; }();
+  return !off && (long long)g.B * g.L * g.H * g.W >= (1LL << 22);
+}
+
+// joins on every exit path (an early error return must not leave the side stream dangling off `s`, least of all in a capture)
+struct ForkGuard {
+  SideStream ss{};
+  cudaStream_t s = nullptr;
+  bool active = false;
+  int fork(cudaStream_t main) {
+    if (int rc = side_stream(&ss)) return rc;
+    if (int rc = side_fork(ss, main)) return rc;
+    s = main; active = true;
+    return MGR_OK;
+  }
+  cudaStream_t side_or(cudaStream_t main) const { return active ? ss.side : main; }
+  int join() {
+    if (!active) return MGR_OK;
+    active = false;
+    return side_join(ss, s);
+  }
+  ~ForkGuard() { if (active) (void)side_join(ss, s); }
+};
+
 // 16-bit footprints are staged in 8-texel items (128-bit loads) when every row of every layer starts on a 16-byte
 // boundary and the rectangles are multiples of 8 texels (render_ws.cuh: stage_flat); narrow items otherwise
 template <typename T>
@@ -137,9 +165,15 @@ int launch_forward_tiled(const void* x, const SrcLayers& src, const float* theta
       MGR_CUDA(cudaGetLastError());
       count_launch();
     }
+    // the two families partition the batch: the general kernel goes to the side stream, the stencil kernel stays on `s`
+    // (big batches only: the fork / join is four runtime calls)
+    ForkGuard fg;
+    if (stencil && use_side_stream(g))
+      if (int rc = fg.fork(s)) return rc;
+    cudaStream_t sg = fg.side_or(s);
     auto launch = [&](auto kern) -> int {
       if (int rc = ensure_dynamic_smem(kern, smem_w)) return rc;
-      kern<<<grid, kWsThreads, smem_w, s>>>((const T*)x, src, theta, (T*)out, (SA*)sav, with_vec8<T>(src, g), stencil, flags);
+      kern<<<grid, kWsThreads, smem_w, sg>>>((const T*)x, src, theta, (T*)out, (SA*)sav, with_vec8<T>(src, g), stencil, flags);
       return MGR_OK;
     };
     if (int rc = sav ? launch(render_fwd_ws<T, true, kRagged>) : launch(render_fwd_ws<T, false, kRagged>)) return rc;
@@ -163,7 +197,7 @@ int launch_forward_tiled(const void* x, const SrcLayers& src, const float* theta
     }
     MGR_CUDA(cudaGetLastError());
     count_launch();
-    return MGR_OK;
+    return fg.join();                                       // both kernels are queued: `s` continues when the side stream is done too
   }
   if constexpr (sizeof(T) == 4) {               // fp32: one launch per path (see render_fwd.cuh)
     if (sav) render_fwd_general_only<T, true, kRagged><<<grid, kTiledThreads, smem_a, s>>>((const T*)x, src, theta, (T*)out, (SA*)sav, g, stencil);
@@ -264,6 +298,11 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
   dim3 grid((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B);
   const int shift = debug_path() != 2;
   const size_t gp_bytes = sizeof(float4) * kPx * kTiledThreads;
+  // the general passes (side stream) and the stencil backward (`s`) touch disjoint samples; see SideStream
+  ForkGuard fg;
+  if (shift && use_side_stream(g))
+    if (int rc = fg.fork(s)) return rc;
+  cudaStream_t sg = fg.side_or(s);
   // warp-specialised pass 1 for 16-bit tensors; fp32 keeps the two-barrier kernel (its 45 KB slots leave room for one
   // CTA per SM only next to the transmittance stash: measured 4-12 % slower)
   if (debug_path() != 3 && sizeof(T) == 2) {
@@ -272,8 +311,8 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
     const size_t smem = ws_bwd_smem_bytes(g.L, sizeof(Vec), gp_smem);
     auto launch = [&](auto kern) -> int {
       if (int rc = ensure_dynamic_smem(kern, smem)) return rc;
-      kern<<<grid, kWsThreads, smem, s>>>((const T*)x, src, theta, (const T*)out, (const T*)gout, (const SA*)sav, rec, gp,
-                                          nt ? gtheta : nullptr, with_vec8<T>(src, g), sflag, shift);
+      kern<<<grid, kWsThreads, smem, sg>>>((const T*)x, src, theta, (const T*)out, (const T*)gout, (const SA*)sav, rec, gp,
+                                           nt ? gtheta : nullptr, with_vec8<T>(src, g), sflag, shift);
       return MGR_OK;
     };
     int rc;
@@ -289,8 +328,8 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
     if (gp_smem) smem += gp_bytes;
     auto launch = [&](auto kern) -> int {
       if (int rc = ensure_dynamic_smem(kern, smem)) return rc;
-      kern<<<grid, kTiledThreads, smem, s>>>((const T*)x, src, theta, (const T*)out, (const T*)gout, (const SA*)sav, rec, gp,
-                                             nt ? gtheta : nullptr, g, sflag, shift);
+      kern<<<grid, kTiledThreads, smem, sg>>>((const T*)x, src, theta, (const T*)out, (const T*)gout, (const SA*)sav, rec, gp,
+                                              nt ? gtheta : nullptr, g, sflag, shift);
       return MGR_OK;
     };
     int rc;
@@ -305,10 +344,10 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
     const long long blocks = (long long)((g.W + 31) / 32) * ((g.H + 31) / 32) * g.B * g.L;
     if (blocks >= 16384) {
       dim3 grid2((g.W + 31) / 32, (g.H + 31) / 32, g.B * g.L);
-      render_bwd_pass2<T, kRagged, 16><<<grid2, 256, 0, s>>>(inv, work, wcnt, rec, gp, (T*)gx, dst, g);
+      render_bwd_pass2<T, kRagged, 16><<<grid2, 256, 0, sg>>>(inv, work, wcnt, rec, gp, (T*)gx, dst, g);
     } else {
       dim3 grid2((g.W + 63) / 64, (g.H + 15) / 16, g.B * g.L);
-      render_bwd_pass2<T, kRagged, 32><<<grid2, 256, 0, s>>>(inv, work, wcnt, rec, gp, (T*)gx, dst, g);
+      render_bwd_pass2<T, kRagged, 32><<<grid2, 256, 0, sg>>>(inv, work, wcnt, rec, gp, (T*)gx, dst, g);
     }
     MGR_CUDA(cudaGetLastError());
     count_launch();
@@ -356,7 +395,7 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
     MGR_CUDA(cudaGetLastError());
     count_launch();
   }
-  return MGR_OK;
+  return fg.join();
 }
 
 template <typename T>

@@ -33,6 +33,35 @@ int cuda_fail(cudaError_t e, const char* what) {
   return fail(MGR_ERR_CUDA_BASE + (int)e, "%s: %s", what, cudaGetErrorString(e));
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int side_stream(SideStream* out) {
+  constexpr int kMaxDev = 64;
+  thread_local SideStream cache[kMaxDev];
+  thread_local bool have[kMaxDev] = {};
+  int dev = 0;
+  MGR_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= kMaxDev) return fail(MGR_ERR_UNSUPPORTED, "device ordinal %d", dev);
+  if (!have[dev]) {
+    SideStream ss;
+    MGR_CUDA(cudaStreamCreateWithFlags(&ss.side, cudaStreamNonBlocking));
+    MGR_CUDA(cudaEventCreateWithFlags(&ss.fork_ev, cudaEventDisableTiming));
+    MGR_CUDA(cudaEventCreateWithFlags(&ss.join_ev, cudaEventDisableTiming));
+    cache[dev] = ss;
+    have[dev] = true;
+  }
+  *out = cache[dev];
+  return MGR_OK;
+}
+int side_fork(const SideStream& ss, cudaStream_t s) {
+  MGR_CUDA(cudaEventRecord(ss.fork_ev, s));
+  MGR_CUDA(cudaStreamWaitEvent(ss.side, ss.fork_ev, 0));
+  return MGR_OK;
+}
+int side_join(const SideStream& ss, cudaStream_t s) {
+  MGR_CUDA(cudaEventRecord(ss.join_ev, ss.side));
+  MGR_CUDA(cudaStreamWaitEvent(s, ss.join_ev, 0));
+  return MGR_OK;
+}
 int debug_path() { return g_debug_path.load(std::memory_order_relaxed); }
 }  // namespace mgr
 
