@@ -355,7 +355,10 @@ def run_cuda_arm(args, wl):
                                      "frac": (fb + bb) / 1e9 / (ms_T / args.steps / 1e3) / peak,
                                      "traffic": tr.get("translation_fwd_bwd"),
                                      "note": "same workload with the placements STNv2c emits (pure translations, "
-                                             "U(-1,1)); kernels only, inputs resident"},
+                                             "U(-1,1)); kernels only, inputs resident.  `frac` counts the ALGORITHMIC bytes "
+                                             "(every texel once); shifts this large push half of every layer off the canvas and "
+                                             "the kernels skip what no pixel samples, so the bytes actually moved (`traffic`, ncu) "
+                                             "are fewer"},
                 "fp32_storage": None if thr_32 is None else {
                     "value": thr_32 / 1e6, "unit": UNIT, "ms_per_step": ms_32,
                     "frac": sum(algorithmic_bytes(B, L, H, W, 4, 4, 4)) / 1e9 / (ms_32 / 1e3) / peak,

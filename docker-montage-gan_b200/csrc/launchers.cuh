@@ -161,7 +161,7 @@ int launch_forward_tiled(const void* x, const SrcLayers& src, const float* theta
     int* flags = nullptr;
     if (stencil && sav) {
       flags = reinterpret_cast<int*>(reinterpret_cast<char*>(sav) + saved_alpha_flags_offset(g.B, g.L, g.H, g.W, sizeof(SA)));
-      sample_shift_flags_kernel<<<(g.B + 255) / 256, 256, 0, s>>>(theta, g.B, g.L, flags);
+      sample_shift_flags_kernel<<<(g.B + 7) / 8, 256, 0, s>>>(theta, g.B, g.L, flags);
       MGR_CUDA(cudaGetLastError());
       count_launch();
     }

@@ -299,14 +299,16 @@ static __global__ void inverse_plans_kernel(const float* __restrict__ theta, Inv
   plans[k] = q;
 }
 
-// The forward's flags: one thread per sample, flags[b] = every layer of the sample is a pure translation.
+// The forward's flags: one warp per sample, a lane per layer (L <= 32 on the tiled path): flags[b] = every layer of the
+// sample is a pure translation.  One round of loads instead of a thread walking its sample's 6 L floats (6.2 -> ~3 us).
 static __global__ void __launch_bounds__(256)
 sample_shift_flags_kernel(const float* __restrict__ theta, int B, int L, int* __restrict__ flags) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
-  int all = 1;
-  for (int l = 0; l < L; ++l) all &= is_pure_shift(theta + ((long long)b * L + l) * 6) ? 1 : 0;
-  flags[b] = all;
+  bool ok = true;
+  for (int l = lane; l < L; l += 32) ok = ok && is_pure_shift(theta + ((long long)b * L + l) * 6);
+  const bool all = __all_sync(0xffffffffu, ok);
+  if (lane == 0) flags[b] = all ? 1 : 0;
 }
 
 // One CTA.  Phase 1, a thread per sample: are all of its layers pure translations?  (those samples belong to

@@ -140,6 +140,7 @@ __device__ __forceinline__ void left_pairs(float gl, f32x2 C0, f32x2 C1, f32x2& 
 
 // four adjacent texels of one row, element k written iff ok[k]: 32-bit stores where two neighbours share an aligned word
 // (`odd`: the first texel's column is odd), 16-bit stores for the rest.  Rows start on even element offsets (W % 4 == 0).
+// Predicated per element on purpose: a masked fast / slow split sent most warps of a border tile down both paths (+16 %).
 template <typename T>
 __device__ __forceinline__ void store4(T* o, const float (&v)[4], const bool (&ok)[4], bool odd) {
   if constexpr (sizeof(T) == 4) {
@@ -275,9 +276,10 @@ render_bwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const __grid_cons
   f32x2 msk[2][2], xq[2];
   float yr[2];
   if (kNeedTheta) {
+    const float inv_w = 1.f / (float)g.W, inv_h = 1.f / (float)g.H;   // normalised pixel centres (2k + 1) / n - 1, to an ulp
     float mc[4], xs[4];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) { mc[k] = (4 * tx + k >= 1) ? 1.f : 0.f; xs[k] = norm_coord(jt + k, g.W); }
+    for (int k = 0; k < 4; ++k) { mc[k] = (4 * tx + k >= 1) ? 1.f : 0.f; xs[k] = fmaf((float)(2 * (jt + k) + 1), inv_w, -1.f); }
     f32x2 m0, m1;
     strip_pack<T>(mc, m0, m1);
     strip_pack<T>(xs, xq[0], xq[1]);
@@ -285,7 +287,7 @@ render_bwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const __grid_cons
     for (int r = 0; r < 2; ++r) {
       const float mr = (2 * ty + r >= 1) ? 1.f : 0.f;
       msk[r][0] = mul2(m0, bc(mr)); msk[r][1] = mul2(m1, bc(mr));
-      yr[r] = norm_coord(it0 + r, g.H);
+      yr[r] = fmaf((float)(2 * (it0 + r) + 1), inv_h, -1.f);
     }
   }
 

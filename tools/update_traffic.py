@@ -49,7 +49,7 @@ data = json.load(open(path)) if os.path.exists(path) else {}
 data[workload] = {
     "bytes": total("render_bwd_pass1", "render_bwd_pass2", "placements", "inverse_plans", "sample_flags"),
     "forward": total("render_fwd_ws", "render_fwd_general_only", "render_fwd<"),
-    "translation_fwd_bwd": total("render_fwd_stencil_only", "render_bwd_shift"),
+    "translation_fwd_bwd": total("render_fwd_stencil_only", "render_fwd_shift_tma", "render_bwd_shift"),
     "per_kernel": avg,
     "source": f"ncu --set full, {rep}: dram__bytes_read.sum + dram__bytes_write.sum per active launch"}
 json.dump(data, open(path, "w"), indent=1)
