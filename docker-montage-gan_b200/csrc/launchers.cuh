@@ -353,18 +353,20 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
     count_launch();
   }
   bool shift_tma = false;
-  if constexpr (!kRagged && sizeof(T) == 2) {
-    // canvas layout, 16-bit tensors, contiguous grad_x: the stencil backward on TMA box copies (render_shift_tma_bwd.cuh)
+  if constexpr (!kRagged) {
+    // canvas layout, contiguous grad_x: the stencil backward on TMA box copies (render_shift_tma_bwd.cuh)
     CUtensorMap xmap, amap, gmap, omap;
     const BwdSmem lay = bwd_tma_layout<T>(g.L);
-    if (shift && debug_path() != 4 && (size_t)lay.total <= 100 * 1024 && bwd_tma_maps<T>(&xmap, &amap, &gmap, &omap, x, sav, gout, out, g)) {
+    if (shift && debug_path() != 4 && (size_t)lay.total <= 100 * 1024 && (!nx || reinterpret_cast<uintptr_t>(dst.s[0].ptr) % 16 == 0) &&
+        bwd_tma_maps<T>(&xmap, &amap, &gmap, &omap, x, sav, gout, out, g)) {
       shift_tma = true;
       dim3 grid4((g.W + 1 + kBAncW - 1) / kBAncW, (g.H + 1 + kBAncH - 1) / kBAncH, g.B);
       const DstLayer& d0 = dst.s[0];
       const long long gx_sl = g.L > 1 ? (reinterpret_cast<T*>(dst.s[1].ptr) - reinterpret_cast<T*>(d0.ptr)) : 0;
       auto launch4 = [&](auto kern) -> int {
         if (int rc = ensure_dynamic_smem(kern, (size_t)lay.total)) return rc;
-        kern<<<grid4, kBThreads, lay.total, s>>>(xmap, amap, gmap, omap, theta, (T*)d0.ptr, d0.sb, gx_sl, nt ? gtheta : nullptr, g, sflag);
+        kern<<<grid4, kBThreads, lay.total, s>>>(xmap, amap, gmap, omap, theta, (T*)d0.ptr, d0.sb, gx_sl, nt ? gtheta : nullptr, g, sflag,
+                                                 (const SA*)sav, (const T*)gout, (const T*)out, reinterpret_cast<float*>(rec));
         return MGR_OK;
       };
       int rc;

@@ -64,12 +64,25 @@ __device__ __forceinline__ bool shift_box_misses(int x0, int y0, int W, int H) {
 template <typename T> struct Row5;
 template <> struct Row5<float> {
   static constexpr bool kStrided = false;
+  // R = 0..3: e0 at compile-time offset R of the aligned 16-byte chunk at p; R = -1: the offset is `off` at run time (CTA-uniform):
+  // eleven selects instead of a copy of the layer body per offset (the backward's loop has to fit the instruction cache)
   template <int R>
-  static __device__ __forceinline__ void taps(const float* p, int, f32x2& L0, f32x2& L1, f32x2& R0, f32x2& R1) {
+  static __device__ __forceinline__ void taps(const float* p, int off, f32x2& L0, f32x2& L1, f32x2& R0, f32x2& R1) {
     const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
     const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-    L0 = pk(v[R], v[R + 1]); L1 = pk(v[R + 2], v[R + 3]);
-    R0 = pk(v[R + 1], v[R + 2]); R1 = pk(v[R + 3], v[R + 4]);
+    if constexpr (R < 0) {
+      const bool two = off & 2, one = off & 1;
+      float w[6], e[5];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) w[k] = two ? v[k + 2] : v[k];
+#pragma unroll
+      for (int k = 0; k < 5; ++k) e[k] = one ? w[k + 1] : w[k];
+      L0 = pk(e[0], e[1]); L1 = pk(e[2], e[3]); R0 = pk(e[1], e[2]); R1 = pk(e[3], e[4]);
+    } else {
+      constexpr int Q = R < 0 ? 0 : R;
+      L0 = pk(v[Q], v[Q + 1]); L1 = pk(v[Q + 2], v[Q + 3]);
+      R0 = pk(v[Q + 1], v[Q + 2]); R1 = pk(v[Q + 3], v[Q + 4]);
+    }
   }
 };
 // 16-bit storage: `p` points at the EVEN element at or left of e0 (a 32-bit word boundary), `sh` = 16 if e0 is the odd half

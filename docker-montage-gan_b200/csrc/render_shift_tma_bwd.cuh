@@ -63,10 +63,17 @@ __host__ __device__ inline BwdSmem bwd_tma_layout(int L) {
   BwdSmem m;
   m.x = 0;
   m.gout = m.x + kBStages * Box::kXStage;
-  m.out = m.gout + Box::kGStage;
-  m.gp = m.out + Box::kGStage;
-  m.alpha = m.gp + Box::kGPBytes;
-  m.red = m.alpha + Box::alpha_bytes(L);
+  if (sizeof(T) == 4) {                    // fp32: no pixel-space boxes (see kGlobalT); `gout` is the record area, no alpha tile
+    m.out = m.gout;
+    m.gp = m.gout + Box::kRecBytes;
+    m.alpha = m.gp + Box::kGPBytes;
+    m.red = m.alpha;
+  } else {
+    m.out = m.gout + Box::kGStage;
+    m.gp = m.out + Box::kGStage;
+    m.alpha = m.gp + Box::kGPBytes;
+    m.red = m.alpha + Box::alpha_bytes(L);
+  }
   m.plan = m.red + L * (kBConsumers / 32) * 8 * (int)sizeof(float);
   m.bars = m.plan + L * (int)sizeof(ShiftPlan);
   m.total = m.bars + 64;
@@ -138,16 +145,14 @@ __device__ __forceinline__ void left_pairs(float gl, f32x2 C0, f32x2 C1, f32x2& 
   else { L0 = pk(gl, lo(C0)); L1 = pk(hi(C0), lo(C1)); }               // C0 = (g0, g1), C1 = (g2, g3): lefts (gl, g0), (g1, g2)
 }
 
-// four adjacent texels of one row, element k written iff ok[k]: 32-bit stores where two neighbours share an aligned word
-// (`odd`: the first texel's column is odd), 16-bit stores for the rest.  Rows start on even element offsets (W % 4 == 0).
+__device__ __forceinline__ void st_vec2(float* p, const float (&v)[2]) { *reinterpret_cast<float2*>(p) = make_float2(v[0], v[1]); }
+
+// four adjacent texels of one row, element k written iff ok[k]: one double-width store where two neighbours share an aligned
+// word of twice the element size (`odd`: the first texel's column is odd), single-element stores for the rest.  Rows start on even element offsets (W % 4 == 0).
 // Predicated per element on purpose: a masked fast / slow split sent most warps of a border tile down both paths (+16 %).
 template <typename T>
 __device__ __forceinline__ void store4(T* o, const float (&v)[4], const bool (&ok)[4], bool odd) {
-  if constexpr (sizeof(T) == 4) {
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      if (ok[k]) st(o + k, v[k]);
-  } else {
+  {
     auto pair = [&](int k) {                                  // elements k, k + 1 share a word
       if (ok[k] && ok[k + 1]) { const float t[2] = {v[k], v[k + 1]}; st_vec2(o + k, t); }
       else { if (ok[k]) st(o + k, v[k]); if (ok[k + 1]) st(o + k + 1, v[k + 1]); }
@@ -156,16 +161,23 @@ __device__ __forceinline__ void store4(T* o, const float (&v)[4], const bool (&o
     else { pair(0); pair(2); }
   }
 }
-
 template <typename T, bool kNeedX, bool kNeedTheta>
 __global__ void __launch_bounds__(kBThreads, MGR_STB_BLOCKS)
 render_bwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap amap,
                      const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUtensorMap omap,
                      const float* __restrict__ theta, T* __restrict__ gx, long long gx_sb, long long gx_sl,
-                     float* __restrict__ gtheta, Geometry g, const int* __restrict__ sample_all_shift) {
+                     float* __restrict__ gtheta, Geometry g, const int* __restrict__ sample_all_shift,
+                     const typename SavedAlpha<T>::type* __restrict__ sav, const T* __restrict__ gout, const T* __restrict__ outp,
+                     float* __restrict__ tws) {
   using Box = BwdBox<T>;
   using SA = typename SavedAlpha<T>::type;
   constexpr int BW = Box::W;
+  // fp32 tensors: the alpha / grad_out / out boxes and fp32 transmittances of a tile would leave room for ONE CTA per SM, so
+  // the pre-pass reads the tile's pixels straight from global memory (once per CTA) and parks T_l in the workspace (`tws`, the
+  // record area of the general passes, 8 bytes per layer-pixel: a translation sample's [L][H*W] floats take the first half of ITS OWN
+  // slice, so nothing collides with the general samples' records being written on the other stream); the layer loop reads T_l back
+  // (L2 hits, issued before the layer's sampling).  Pixels shared by overlapping tiles get the same bits from each of them.
+  constexpr bool kGlobalT = sizeof(T) == 4;
   const int b = blockIdx.z;
   if (!sample_all_shift[b]) return;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -188,10 +200,12 @@ render_bwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const __grid_cons
     for (int s = 0; s < kBStages; ++s) { tma_mbar_init(&full[s], 1); tma_mbar_init(&empty[s], kBConsumers / 32); }
     tma_mbar_init(bar0, 1);
     tma_fence_barrier_init();
-    tma_mbar_expect_tx(bar0, (uint32_t)(Box::kPPlane * g.L * (int)sizeof(SA) + 2 * Box::kGBytes));
-    tma_load_4d(atile, &amap, bar0, xp, i0, 0, b);
-    tma_load_4d(smem + lay.gout, &gmap, bar0, xp, i0, 0, b);
-    tma_load_4d(smem + lay.out, &omap, bar0, xp, i0, 0, b);
+    if (!kGlobalT) {
+      tma_mbar_expect_tx(bar0, (uint32_t)(Box::kPPlane * g.L * (int)sizeof(SA) + 2 * Box::kGBytes));
+      tma_load_4d(atile, &amap, bar0, xp, i0, 0, b);
+      tma_load_4d(smem + lay.gout, &gmap, bar0, xp, i0, 0, b);
+      tma_load_4d(smem + lay.out, &omap, bar0, xp, i0, 0, b);
+    }
   }
   for (int l = tid; l < g.L; l += kBThreads) splan[l] = make_shift_plan(theta + ((long long)b * g.L + l) * 6, g.H, g.W);
   if (kNeedTheta)
@@ -221,25 +235,60 @@ render_bwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const __grid_cons
   const float zs = g.m11 ? 0.5f : 1.f;
   const f32x2 zs2 = bc(zs), zb2 = bc(g.m11 ? 0.5f : 0.f);
 
-  // ---- pre-pass: T_l in place of the alpha samples, (G_P, G_A) per pixel ----
-  tma_mbar_wait(bar0, 0);
+  // ---- pre-pass: T_l in place of the alpha samples (fp32: in the workspace), (G_P, G_A) per pixel ----
+  const int hw = g.H * g.W;
+  bool livep[2][4];                                           // the strip's pixels that exist
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) livep[r][k] = (unsigned)(jt + k) < (unsigned)g.W && (unsigned)(it0 + r) < (unsigned)g.H;
+  const int pix0 = it0 * g.W + jt;                            // the strip's first pixel inside a plane (only used where live)
+  if (!kGlobalT) tma_mbar_wait(bar0, 0);
   {
     float A[2][4], Tc[2][4];
 #pragma unroll
     for (int r = 0; r < 2; ++r)
 #pragma unroll
       for (int k = 0; k < 4; ++k) { A[r][k] = 0.f; Tc[r][k] = 1.f; }
-    for (int l = g.L - 1; l >= 0; --l) {
-      SA* al = atile + l * Box::kPPlane + poff;
+    if constexpr (kGlobalT) {
+      const SA* sb_ = sav + (long long)b * g.L * hw + pix0;
+      float* tb_ = tws + 2LL * b * g.L * hw + pix0;          // the first half of THIS sample's record area: [L][H*W] floats
+      float an[2][4];                                         // next layer's alphas: loaded one layer ahead of their use
 #pragma unroll
       for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const float a = sa_to_float(al[r * BW + k]);
-          al[r * BW + k] = float_to_sa<SA>(Tc[r][k]);
-          A[r][k] = fmaf(Tc[r][k], a, A[r][k]);
-          Tc[r][k] *= 1.f - a;
-        }
+        for (int k = 0; k < 4; ++k) an[r][k] = livep[r][k] ? __ldg(sb_ + (long long)(g.L - 1) * hw + r * g.W + k) : 0.f;
+      for (int l = g.L - 1; l >= 0; --l) {
+        float ac[2][4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            ac[r][k] = an[r][k];
+            if (l > 0) an[r][k] = livep[r][k] ? __ldg(sb_ + (long long)(l - 1) * hw + r * g.W + k) : 0.f;
+          }
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            if (livep[r][k]) tb_[(long long)l * hw + r * g.W + k] = Tc[r][k];
+            A[r][k] = fmaf(Tc[r][k], ac[r][k], A[r][k]);
+            Tc[r][k] *= 1.f - ac[r][k];
+          }
+      }
+    } else {
+      for (int l = g.L - 1; l >= 0; --l) {
+        SA* al = atile + l * Box::kPPlane + poff;
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float a = sa_to_float(al[r * BW + k]);
+            al[r * BW + k] = float_to_sa<SA>(Tc[r][k]);
+            A[r][k] = fmaf(Tc[r][k], a, A[r][k]);
+            Tc[r][k] *= 1.f - a;
+          }
+      }
     }
     const float gs = g.m11 ? 2.f : 1.f;                       // d out / d o
     const float is = g.m11 ? 0.5f : 1.f, ib = g.m11 ? 0.5f : 0.f;
@@ -250,12 +299,24 @@ render_bwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const __grid_cons
       for (int k = 0; k < 4; ++k) {
         const int e = poff + r * BW + k;
         gpv[0][k] = gpv[1][k] = gpv[2][k] = gpv[3][k] = 0.f;
-        if (A[r][k] != 0.f) {
+        if (A[r][k] != 0.f) {                                 // (a pixel outside the image has A == 0)
           const float inv = 1.f / A[r][k];
-          const float g0 = gs * t_to_float(gtile[e]), g1 = gs * t_to_float(gtile[e + Box::kPPlane]),
-                      g2 = gs * t_to_float(gtile[e + 2 * Box::kPPlane]), g3 = gs * t_to_float(gtile[e + 3 * Box::kPPlane]);
-          const float o0 = fmaf(t_to_float(otile[e]), is, ib), o1 = fmaf(t_to_float(otile[e + Box::kPPlane]), is, ib),
-                      o2 = fmaf(t_to_float(otile[e + 2 * Box::kPPlane]), is, ib);
+          float gr_[4], or_[3];
+          if constexpr (kGlobalT) {
+            const T* gq = gout + (long long)b * 4 * hw + pix0 + r * g.W + k;
+            const T* oq = outp + (long long)b * 4 * hw + pix0 + r * g.W + k;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) gr_[c] = ld(gq + c * hw);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) or_[c] = ld(oq + c * hw);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) gr_[c] = t_to_float(gtile[e + c * Box::kPPlane]);
+#pragma unroll
+            for (int c = 0; c < 3; ++c) or_[c] = t_to_float(otile[e + c * Box::kPPlane]);
+          }
+          const float g0 = gs * gr_[0], g1 = gs * gr_[1], g2 = gs * gr_[2], g3 = gs * gr_[3];
+          const float o0 = fmaf(or_[0], is, ib), o1 = fmaf(or_[1], is, ib), o2 = fmaf(or_[2], is, ib);
           gpv[0][k] = g0 * inv; gpv[1][k] = g1 * inv; gpv[2][k] = g2 * inv;
           gpv[3][k] = g3 - fmaf(g2, o2, fmaf(g1, o1, g0 * o0)) * inv;
         }
@@ -296,7 +357,6 @@ render_bwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const __grid_cons
   for (int r = 0; r < 2; ++r) q[r][0] = q[r][1] = bc(0.f);
   const int toff = (2 * ty) * BW + 4 * tx;
   T* gxb = gx + (long long)b * gx_sb;
-  const int hw = g.H * g.W;
   unsigned cmask = 0, rmask = 0;                              // anchors of the strip this CTA owns and that exist (a <= W, b <= H)
 #pragma unroll
   for (int k = 0; k < 4; ++k) cmask |= (4 * tx + k >= 1 && jt + k <= g.W) ? (1u << k) : 0u;
@@ -350,8 +410,16 @@ render_bwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const __grid_cons
     }
     const f32x2 fx2 = bc(sp.fx), fy2 = bc(sp.fy);
     const T* p = stage + toff + (sizeof(T) == 2 ? (dx0 & ~1) : 0);   // 16-bit: the even element at or left of e0 (Row5)
-    const int sh = (dx0 & 1) * 16;
+    const int sh = sizeof(T) == 2 ? (dx0 & 1) * 16 : dx0;           // 16-bit: funnel shift; fp32: offset inside the aligned chunk
     const SA* tl = atile + l * Box::kPPlane + poff;
+    float tg[2][4];                                           // fp32: T_l from the workspace, in flight while alpha is sampled
+    if constexpr (kGlobalT) {
+      const float* tq = tws + (2LL * b * g.L + l) * hw + pix0;
+#pragma unroll
+      for (int r = 0; r < 2; ++r)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tg[r][k] = livep[r][k] ? __ldcg(tq + r * g.W + k) : 1.f;
+    }
     float* recw = rec + (it & 1) * 2 * kBH * kBW;               // this layer's record buffer
 
     float th6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -365,7 +433,7 @@ render_bwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const __grid_cons
         for (int r = 0; r < 2; ++r) {
           float tv[4];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) tv[k] = sa_to_float(tl[r * BW + k]);
+          for (int k = 0; k < 4; ++k) tv[k] = kGlobalT ? tg[r][k] : sa_to_float(tl[r * BW + k]);
           strip_pack<T>(tv, tt[r][0], tt[r][1]);
           a[r][0] = fma2(v[r][0], zs2, zb2); a[r][1] = fma2(v[r][1], zs2, zb2);
           ta[r][0] = mul2(tt[r][0], a[r][0]); ta[r][1] = mul2(tt[r][1], a[r][1]);
@@ -431,13 +499,7 @@ render_bwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const __grid_cons
         th6[5] = sy0 + sy1;
       }
     };
-    if constexpr (sizeof(T) == 2) body(std::integral_constant<int, -1>{});
-    else switch (dx0 & 3) {
-      case 0: body(std::integral_constant<int, 0>{}); break;
-      case 1: body(std::integral_constant<int, 1>{}); break;
-      case 2: body(std::integral_constant<int, 2>{}); break;
-      default: body(std::integral_constant<int, 3>{}); break;
-    }
+    body(std::integral_constant<int, -1>{});               // one body for every alignment of the box (Row5)
     __syncwarp();
     if (lane == 0) tma_mbar_arrive(&empty[s]);                // the x box is free for the copy after next
     ++it;
@@ -524,6 +586,7 @@ inline bool bwd_tma_maps(CUtensorMap* xmap, CUtensorMap* amap, CUtensorMap* gmap
                          const void* gout, const void* out, const Geometry& g) {
   using Box = BwdBox<T>;
   if (!shift_tma_x_map<T>(xmap, x, g, Box::W, Box::kXRows)) return false;
+  if (sizeof(T) == 4) { *amap = *gmap = *omap = *xmap; return true; }     // fp32 reads the pixel-space tensors directly (kGlobalT)
   const long long hw = (long long)g.H * g.W;
   const long long ad[4] = {g.W, g.H, g.L, g.B}, as[4] = {1, g.W, hw, hw * g.L};
   const int ab[4] = {Box::W, kBH, g.L, 1};

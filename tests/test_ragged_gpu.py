@@ -97,16 +97,18 @@ def test_ragged_equals_canvas_path_on_padded_tensor(canvas, sizes, tf, dtype):
     out, gxs, gt = _run_ragged(layers, theta, go, canvas)
     out_c, gx_c, gt_c = _run_canvas(padded, theta, go)
     assert torch.equal(out, out_c)                                      # same texels, same arithmetic
-    # 16-bit canvases of pure translations take the backward on TMA box copies (render_shift_tma_bwd.cuh: transmittances
-    # kept in fp16, another summation order), ragged stacks the staged stencil kernel: equal to storage rounding there,
-    # bit for bit everywhere else
-    tma = dtype != torch.float32 and tf == "T"
+    # canvases of pure translations take the backward on TMA box copies (render_shift_tma_bwd.cuh: another summation order,
+    # and fp16 transmittances for 16-bit tensors), ragged stacks the staged stencil kernel: equal to rounding there, bit for
+    # bit everywhere else
+    tma = tf == "T"
+    # (fp32: these stacks have no covering layer, so G_P = g / A is formed with A down to ~1e-3 and two summation orders part by 1e-4)
+    tol = {torch.float32: 5e-4, torch.bfloat16: 2.0 ** -6, torch.float16: 2.0 ** -9}[dtype]
     for g, gc in zip(gxs, _crop(gx_c, sizes, canvas)):
         if tma:
-            assert rel_err(g.float().numpy(), gc.float().numpy()) <= (2.0 ** -6 if dtype == torch.bfloat16 else 2.0 ** -9)
+            assert rel_err(g.float().numpy(), gc.float().numpy()) <= tol
         else:
             assert torch.equal(g, gc)
-    assert rel_err(gt.numpy(), gt_c.numpy()) < (2e-2 if tma else 1e-5)  # atomics: summation order only
+    assert rel_err(gt.numpy(), gt_c.numpy()) < ((2e-3 if dtype == torch.float32 else 2e-2) if tma else 1e-5)  # atomics: summation order only
 
 
 def test_ragged_range01_and_partial_grads():

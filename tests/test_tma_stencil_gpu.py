@@ -45,7 +45,7 @@ def _run(x, th, go, in_range, dtype, path):
 @pytest.mark.parametrize("in_range", ["m11", "01"])
 @pytest.mark.parametrize("shape", [(2, 7, 64, 128), (1, 5, 40, 72), (2, 3, 100, 200), (1, 9, 16, 64)])
 def test_tma_translation_vs_oracle_fp32(shape, in_range):
-    """fp32 tensors: the TMA forward (the backward stays on the staged kernel) against the fp64 oracle."""
+    """fp32 tensors: TMA forward and backward (transmittances parked in the workspace) against the fp64 oracle."""
     B, L, H, W = shape
     x = synth.make_layers(B, L, H, W, "S", seed=71)
     if in_range == "01":
@@ -56,6 +56,8 @@ def test_tma_translation_vs_oracle_fp32(shape, in_range):
     r64 = R.render_fwd_bwd(x.numpy(), th.numpy(), go.numpy(), in_range, np.float64)
     assert max_abs(out, r64["out"]) < FWD_TOL
     assert rel_err(gx, r64["grad_x"]) < GRAD_TOL
+    old = _run(x, th, go, in_range, torch.float32, 4)        # the staged kernels on the same stack
+    assert max_abs(out, old[0]) <= 1e-6 and rel_err(gx, old[1]) <= 1e-5 and rel_err(gt, old[2]) <= 1e-4
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
