@@ -356,9 +356,16 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
   if constexpr (!kRagged) {
     // canvas layout, contiguous grad_x: the stencil backward on TMA box copies (render_shift_tma_bwd.cuh)
     CUtensorMap xmap, amap, gmap, omap;
-    const BwdSmem lay = bwd_tma_layout<T>(g.L);
+    // transmittances in shared memory (16-bit tensors while two CTAs per SM fit: up to 19 layers; measured at L = 9, where
+    // the tile needs 76 KB: 172 us against 215 us with the workspace variant at three CTAs per SM) or in the workspace
+#ifdef MGR_STB_FORCE_GLOBAL_T
+    const bool global_t = true;
+#else
+    const bool global_t = sizeof(T) == 4 || bwd_tma_layout<T>(g.L, false).total > 100 * 1024;
+#endif
+    const BwdSmem lay = bwd_tma_layout<T>(g.L, global_t);
     if (shift && debug_path() != 4 && (size_t)lay.total <= 100 * 1024 && (!nx || reinterpret_cast<uintptr_t>(dst.s[0].ptr) % 16 == 0) &&
-        bwd_tma_maps<T>(&xmap, &amap, &gmap, &omap, x, sav, gout, out, g)) {
+        bwd_tma_maps<T>(&xmap, &amap, &gmap, &omap, x, sav, gout, out, g, global_t)) {
       shift_tma = true;
       dim3 grid4((g.W + 1 + kBAncW - 1) / kBAncW, (g.H + 1 + kBAncH - 1) / kBAncH, g.B);
       const DstLayer& d0 = dst.s[0];
@@ -370,9 +377,19 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
         return MGR_OK;
       };
       int rc;
-      if (nx && nt) rc = launch4(render_bwd_shift_tma<T, true, true>);
-      else if (nx) rc = launch4(render_bwd_shift_tma<T, true, false>);
-      else rc = launch4(render_bwd_shift_tma<T, false, true>);
+      if constexpr (sizeof(T) == 4) {
+        if (nx && nt) rc = launch4(render_bwd_shift_tma<T, true, true, true>);
+        else if (nx) rc = launch4(render_bwd_shift_tma<T, true, false, true>);
+        else rc = launch4(render_bwd_shift_tma<T, false, true, true>);
+      } else if (global_t) {
+        if (nx && nt) rc = launch4(render_bwd_shift_tma<T, true, true, true>);
+        else if (nx) rc = launch4(render_bwd_shift_tma<T, true, false, true>);
+        else rc = launch4(render_bwd_shift_tma<T, false, true, true>);
+      } else {
+        if (nx && nt) rc = launch4(render_bwd_shift_tma<T, true, true, false>);
+        else if (nx) rc = launch4(render_bwd_shift_tma<T, true, false, false>);
+        else rc = launch4(render_bwd_shift_tma<T, false, true, false>);
+      }
       if (rc) return rc;
       MGR_CUDA(cudaGetLastError());
       count_launch();

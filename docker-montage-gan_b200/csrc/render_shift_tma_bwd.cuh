@@ -58,12 +58,12 @@ struct BwdSmem {          // byte offsets inside the dynamic shared memory windo
   int x, gout, out, gp, alpha, red, plan, bars, total;
 };
 template <typename T>
-__host__ __device__ inline BwdSmem bwd_tma_layout(int L) {
+__host__ __device__ inline BwdSmem bwd_tma_layout(int L, bool global_t) {
   using Box = BwdBox<T>;
   BwdSmem m;
   m.x = 0;
   m.gout = m.x + kBStages * Box::kXStage;
-  if (sizeof(T) == 4) {                    // fp32: no pixel-space boxes (see kGlobalT); `gout` is the record area, no alpha tile
+  if (global_t) {                          // no pixel-space boxes (see kGlobalT); `gout` is the record area, no alpha tile
     m.out = m.gout;
     m.gp = m.gout + Box::kRecBytes;
     m.alpha = m.gp + Box::kGPBytes;
@@ -161,7 +161,7 @@ __device__ __forceinline__ void store4(T* o, const float (&v)[4], const bool (&o
     else { pair(0); pair(2); }
   }
 }
-template <typename T, bool kNeedX, bool kNeedTheta>
+template <typename T, bool kNeedX, bool kNeedTheta, bool kGlobalT>
 __global__ void __launch_bounds__(kBThreads, MGR_STB_BLOCKS)
 render_bwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const __grid_constant__ CUtensorMap amap,
                      const __grid_constant__ CUtensorMap gmap, const __grid_constant__ CUtensorMap omap,
@@ -172,16 +172,17 @@ render_bwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const __grid_cons
   using Box = BwdBox<T>;
   using SA = typename SavedAlpha<T>::type;
   constexpr int BW = Box::W;
-  // fp32 tensors: the alpha / grad_out / out boxes and fp32 transmittances of a tile would leave room for ONE CTA per SM, so
+  // kGlobalT (fp32 tensors, and 16-bit stacks with many layers): the alpha / grad_out / out boxes and the transmittances of a tile
+  // would leave room for too few CTAs per SM, so
   // the pre-pass reads the tile's pixels straight from global memory (once per CTA) and parks T_l in the workspace (`tws`, the
   // record area of the general passes, 8 bytes per layer-pixel: a translation sample's [L][H*W] floats take the first half of ITS OWN
   // slice, so nothing collides with the general samples' records being written on the other stream); the layer loop reads T_l back
   // (L2 hits, issued before the layer's sampling).  Pixels shared by overlapping tiles get the same bits from each of them.
-  constexpr bool kGlobalT = sizeof(T) == 4;
+  static_assert(kGlobalT || sizeof(T) == 2, "fp32 tensors use the workspace for T_l");
   const int b = blockIdx.z;
   if (!sample_all_shift[b]) return;
   extern __shared__ __align__(128) unsigned char smem[];
-  const BwdSmem lay = bwd_tma_layout<T>(g.L);
+  const BwdSmem lay = bwd_tma_layout<T>(g.L, kGlobalT);
   SA* atile = reinterpret_cast<SA*>(smem + lay.alpha);
   const T* gtile = reinterpret_cast<const T*>(smem + lay.gout);
   const T* otile = reinterpret_cast<const T*>(smem + lay.out);
@@ -257,7 +258,7 @@ render_bwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const __grid_cons
 #pragma unroll
       for (int r = 0; r < 2; ++r)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) an[r][k] = livep[r][k] ? __ldg(sb_ + (long long)(g.L - 1) * hw + r * g.W + k) : 0.f;
+        for (int k = 0; k < 4; ++k) an[r][k] = livep[r][k] ? ld_alpha(sb_ + (long long)(g.L - 1) * hw + r * g.W + k) : 0.f;
       for (int l = g.L - 1; l >= 0; --l) {
         float ac[2][4];
 #pragma unroll
@@ -265,7 +266,7 @@ render_bwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const __grid_cons
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             ac[r][k] = an[r][k];
-            if (l > 0) an[r][k] = livep[r][k] ? __ldg(sb_ + (long long)(l - 1) * hw + r * g.W + k) : 0.f;
+            if (l > 0) an[r][k] = livep[r][k] ? ld_alpha(sb_ + (long long)(l - 1) * hw + r * g.W + k) : 0.f;
           }
 #pragma unroll
         for (int r = 0; r < 2; ++r)
@@ -583,10 +584,10 @@ render_bwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const __grid_cons
 // tensor maps of the backward: x {W,H,4,L,B}, saved alpha {W,H,L,B}, grad_out / out {W,H,4,B} (contiguous tensors)
 template <typename T>
 inline bool bwd_tma_maps(CUtensorMap* xmap, CUtensorMap* amap, CUtensorMap* gmap, CUtensorMap* omap, const void* x, const void* sav,
-                         const void* gout, const void* out, const Geometry& g) {
+                         const void* gout, const void* out, const Geometry& g, bool global_t) {
   using Box = BwdBox<T>;
   if (!shift_tma_x_map<T>(xmap, x, g, Box::W, Box::kXRows)) return false;
-  if (sizeof(T) == 4) { *amap = *gmap = *omap = *xmap; return true; }     // fp32 reads the pixel-space tensors directly (kGlobalT)
+  if (global_t) { *amap = *gmap = *omap = *xmap; return true; }           // the pixel-space tensors are read directly (kGlobalT)
   const long long hw = (long long)g.H * g.W;
   const long long ad[4] = {g.W, g.H, g.L, g.B}, as[4] = {1, g.W, hw, hw * g.L};
   const int ab[4] = {Box::W, kBH, g.L, 1};

@@ -19,6 +19,9 @@
 #include "render_shift.cuh"
 #include "render_tiled.cuh"
 
+#ifndef MGR_WS_WAIT_HINT
+#define MGR_WS_WAIT_HINT 0x989680u
+#endif
 #ifndef MGR_WSF_BLOCKS
 #define MGR_WSF_BLOCKS 2
 #endif
@@ -68,11 +71,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {   //
       "{\n"
       ".reg .pred P1;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-      "@P1 bra DONE;\n"
-      "bra LAB_WAIT;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"      // suspend-time hint: a waiting warp sleeps until the phase
+      "@P1 bra DONE;\n"                                                      // completes instead of polling in the issue slots of
+      "bra LAB_WAIT;\n"                                                      // the warps it is waiting for
       "DONE:\n"
-      "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+      "}" ::"r"(smem_u32(bar)), "r"(parity), "r"(MGR_WS_WAIT_HINT) : "memory");
 }
 // Register re-balancing between the roles (whole warpgroups: warps 0-7 consume, 8-11 produce).  The kernel is compiled
 // for kWsThreads x (65536 / (kWsThreads * CTAs per SM)) registers; producers hand theirs back, consumers take them.

@@ -124,6 +124,24 @@ def test_tma_every_alignment_and_border_case(dtype):
         assert not g[:, :, dead_r, :].any(), (l, "rows")
 
 
+def test_tma_16bit_many_layers_uses_the_workspace_for_transmittances():
+    """More than 19 layers of 16-bit tensors: the transmittances no longer fit shared memory next to two CTAs per SM and are
+    parked in the workspace instead (the fp32 policy, kGlobalT); up to 32 layers stay on the box-copy kernels."""
+    for L in (21, 32):
+        B, H, W = 2, 40, 72
+        x = synth.make_layers(B, L, H, W, "S", seed=76).to(torch.bfloat16).float()
+        th = _theta(B, L, 76, 0.6)
+        th[:, 0, 0, 2] = 0.37 * 2 / W
+        th[:, 0, 1, 2] = -0.41 * 2 / H
+        go = synth.make_grad_out(B, H, W, seed=76).to(torch.bfloat16).float()
+        new = _run(x, th, go, "m11", torch.bfloat16, 0)
+        old = _run(x, th, go, "m11", torch.bfloat16, 4)
+        r64 = R.render_fwd_bwd(x.numpy(), th.numpy(), go.numpy(), "m11", np.float64)
+        assert max_abs(new[0], r64["out"]) < 2.5 * 2.0 ** -8
+        assert rel_err(new[1], r64["grad_x"]) < 3 * 2.0 ** -8
+        assert rel_err(new[1], old[1]) <= 3 * 2.0 ** -8 and rel_err(new[2], old[2]) <= 2e-2
+
+
 def test_tma_backward_is_deterministic():
     B, L, H, W = 4, 7, 64, 192
     x = synth.make_layers(B, L, H, W, "S", seed=74)
