@@ -608,14 +608,17 @@ def test_translation_backward_is_deterministic_with_global_gp():
         assert torch.equal(run(), g0)
 
 
+@pytest.mark.parametrize("shape", [(4, 7, 64, 64), (8, 8, 256, 256)])
 @pytest.mark.parametrize("tf", ["I", "T"])
-def test_forward_and_backward_capture_into_a_cuda_graph(tf):
+def test_forward_and_backward_capture_into_a_cuda_graph(tf, shape):
     """include/montage_render.h promises stream-ordered calls without allocations or host reads: the C-ABI forward and
-    backward must record into a CUDA graph and replay on new input contents with the results of an eager run."""
+    backward must record into a CUDA graph and replay on new input contents with the results of an eager run.  The larger
+    shape is past the size from which the general kernels are forked onto the library's side stream (launchers.cuh:
+    use_side_stream): the fork and the join must be captured with the rest."""
     import ctypes
     from montage_gan_b200 import _lib
     lib = _lib.load()
-    B, L, H, W = 4, 7, 64, 64
+    B, L, H, W = shape
     P = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
     x = synth.make_layers(B, L, H, W, "S", seed=41).to(DEV)
     th = synth.make_theta(B, L, tf, seed=41).to(DEV)
