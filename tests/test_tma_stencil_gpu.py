@@ -171,3 +171,12 @@ def test_tma_mixed_batch_and_fallbacks():
     out = mr.render(xv, th.to(DEV), in_range="m11")
     out.backward(go.to(DEV, torch.bfloat16))
     assert max_abs(out.detach().float().cpu().numpy(), old[0]) == 0.0
+    # W + 8 columns allocated: rows start every 2 * (W + 8) bytes, a multiple of 16 -- the tensor map takes the strides as they
+    # are and the view stays on the box-copy kernels: same bits as the contiguous tensor
+    xw8 = torch.full((B, L, 4, H + 3, W + 8), -1.0).to(DEV, torch.bfloat16)
+    xw8[..., :H, :W] = x.to(DEV, torch.bfloat16)
+    xv8 = xw8[..., :H, :W].requires_grad_(True)
+    out8 = mr.render(xv8, th.to(DEV), in_range="m11")
+    out8.backward(go.to(DEV, torch.bfloat16))
+    assert max_abs(out8.detach().float().cpu().numpy(), new[0]) == 0.0
+    assert max_abs(xv8.grad.float().cpu().numpy(), new[1]) == 0.0
