@@ -463,11 +463,26 @@ int backward_typed(const void* x, const float* theta, const void* out, const voi
 template <typename T>
 int launch_warp_forward(const void* x, const float* theta, void* out, const Geometry& g, cudaStream_t s) {
   if (tiled_ok<T>(x, g)) {                                     // staged footprints, one layer per CTA (warp_tiled.cuh)
+    // layers that are pure translations: box copies + planar stencil (render_shift_tma.cuh); the two kernels partition the
+    // layers, on two streams when the batch is big enough for the idle launch to matter (the fork itself costs a general
+    // batch ~10 us at C2 and saves a translation batch ~15: translations are what the placement net emits)
+    CUtensorMap xmap;
+    const bool tma = debug_path() != 4 && debug_path() != 2 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
+                     shift_tma_x_map<T>(&xmap, x, g, ShiftBox<T>::W, ShiftBox<T>::H);
+    ForkGuard fg;
+    if (tma && use_side_stream(g))
+      if (int rc = fg.fork(s)) return rc;
     dim3 gridt((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B * g.L);
-    warp_fwd_tiled<T><<<gridt, kTiledThreads, sizeof(typename Texel<T>::Vec) * kCapTexels, s>>>((const T*)x, theta, (T*)out, g);
+    warp_fwd_tiled<T><<<gridt, kTiledThreads, sizeof(typename Texel<T>::Vec) * kCapTexels, fg.side_or(s)>>>((const T*)x, theta, (T*)out, g, tma ? 1 : 0);
     MGR_CUDA(cudaGetLastError());
     count_launch();
-    return MGR_OK;
+    if (tma) {
+      dim3 grids((g.W + kSW - 1) / kSW, (g.H + kSH - 1) / kSH, g.B * g.L);
+      warp_fwd_shift_tma<T><<<grids, kSConsumers, ShiftBox<T>::kStageBytes, s>>>(xmap, theta, (T*)out, g);
+      MGR_CUDA(cudaGetLastError());
+      count_launch();
+    }
+    return fg.join();
   }
   dim3 grid((g.W + kTileW - 1) / kTileW, (g.H + kTileH - 1) / kTileH, g.B * g.L);
   warp_fwd_kernel<T><<<grid, kDirectThreads, 0, s>>>((const T*)x, theta, (T*)out, g);

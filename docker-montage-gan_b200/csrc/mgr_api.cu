@@ -109,7 +109,7 @@ const char* mgr_build_info(void) {
 const char* mgr_last_error(void) { return g_err; }
 
 int mgr_set_debug_path(int path) {
-  if (path < 0 || path > 3) return fail(MGR_ERR_INVALID_ARGUMENT, "debug path %d unknown", path);
+  if (path < 0 || path > 4) return fail(MGR_ERR_INVALID_ARGUMENT, "debug path %d unknown", path);
   g_debug_path.store(path, std::memory_order_relaxed);
   return MGR_OK;
 }

@@ -389,3 +389,81 @@ inline bool shift_tma_x_map(CUtensorMap* map, const void* x, const Geometry& g, 
 }
 
 }  // namespace mgr
+
+// ---- materialised warp of pure-translation LAYERS (what STNv2c / STNv2b return, fukuwarai/networks.py:250-257, and what
+// random_position computes, custom_utils/image_utils.py:281-294) on the same box copy: one (layer, 64 x 32 tile) per CTA, the
+// raw bilinear lerp of the four planes written out.  The decision is per LAYER here (each layer is warped on its own): CTAs
+// of layers with a general placement leave at once, warp_fwd_tiled makes the opposite choice.  (A CTA walking a band of
+// tiles with the next box in flight was measured no faster: 109 / 171 us against 109 / 163 us, bf16 / fp32 at C2.)
+namespace mgr {
+
+template <typename T>
+__global__ void __launch_bounds__(kSConsumers, 6)
+warp_fwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ theta, T* __restrict__ out, Geometry g) {
+  using Box = ShiftBox<T>;
+  const int n = blockIdx.z;                                   // b * L + l
+  const float* th = theta + (long long)n * 6;
+  if (!is_pure_shift(th)) return;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar;
+  T* stage = reinterpret_cast<T*>(smem);
+  const int tid = threadIdx.x;
+  const int b = n / g.L, l = n - b * g.L;
+  const int j0 = blockIdx.x * kSW, i0 = blockIdx.y * kSH;
+  const ShiftPlan sp = make_shift_plan(th, g.H, g.W);         // every thread: no broadcast needed, the values are uniform
+  const int x0 = j0 + sp.X, y0 = i0 + sp.Y;
+  const bool miss = shift_box_misses(x0, y0, g.W, g.H);
+  const int xa = x0 & ~(Box::kAlign - 1), dx = x0 - xa;
+  if (tid == 0 && !miss) {
+    tma_mbar_init(&bar, 1);
+    tma_fence_barrier_init();
+    tma_mbar_expect_tx(&bar, (uint32_t)Box::kBytes);
+    tma_load_5d(stage, &xmap, &bar, xa, y0, 0, l, b);
+  }
+  __syncthreads();                                            // the barrier is initialised before anyone waits on it
+  const int tx = tid & 15, ty = tid >> 4;
+  const int j = j0 + 4 * tx, i = i0 + 2 * ty;
+  const bool col_live = j < g.W;
+  const int hw = g.H * g.W;
+  T* op = out + (long long)n * 4 * hw + (long long)i * g.W + j;
+  const float padv = g.m11 ? -1.f : 0.f;
+  if (miss) {                                                 // every tap is outside the image: the padding value
+    const float p4[4] = {padv, padv, padv, padv};
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+      if (col_live && i + r < g.H) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) st_vec4<T>(op + c * hw + r * g.W, p4);
+      }
+    return;
+  }
+  tma_mbar_wait(&bar, 0);
+  if (g.m11 && (xa < 0 || xa + Box::W > g.W || y0 < 0 || y0 + Box::H > g.H)) {         // CTA-uniform
+    shift_patch_oob<T>(stage, xa, y0, g.W, g.H, tid);
+    __syncthreads();
+  }
+  const f32x2 fx2 = bc(sp.fx), fy2 = bc(sp.fy);
+  const T* p = stage + (2 * ty) * Box::W + 4 * tx + (dx & ~3);
+  auto body = [&](auto rtag) {
+    constexpr int R = decltype(rtag)::value;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      f32x2 v[2][2];
+      shift_sample_strip<T, R>(p + c * Box::kPlane, 0, fx2, fy2, v);
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float o4[4];
+        strip_unpack<T>(v[r][0], v[r][1], o4);
+        if (col_live && i + r < g.H) st_vec4<T>(op + c * hw + r * g.W, o4);
+      }
+    }
+  };
+  switch (dx & 3) {
+    case 0: body(std::integral_constant<int, 0>{}); break;
+    case 1: body(std::integral_constant<int, 1>{}); break;
+    case 2: body(std::integral_constant<int, 2>{}); break;
+    default: body(std::integral_constant<int, 3>{}); break;
+  }
+}
+
+}  // namespace mgr

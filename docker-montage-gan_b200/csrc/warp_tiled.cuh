@@ -11,8 +11,9 @@ namespace mgr {
 
 template <typename T>
 __global__ void __launch_bounds__(kTiledThreads, 3)
-warp_fwd_tiled(const T* __restrict__ x, const float* __restrict__ theta, T* __restrict__ out, Geometry g) {
+warp_fwd_tiled(const T* __restrict__ x, const float* __restrict__ theta, T* __restrict__ out, Geometry g, int skip_shift) {
   using Vec = typename Texel<T>::Vec;
+  if (skip_shift && is_pure_shift(theta + (long long)blockIdx.z * 6)) return;      // warp_fwd_shift_tma's layer
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Vec* buf = reinterpret_cast<Vec*>(smem_raw);                // [kCapTexels]
   __shared__ LayerPlan plan;

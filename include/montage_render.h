@@ -72,7 +72,7 @@ long long mgr_kernel_launch_count(void);
 /* Testing / A-B timing only: 0 = automatic kernel selection (default), 1 = force the general
  * direct-gather kernels even where the tiled shared-memory kernels apply, 2 = tiled kernels but
  * without the pure-translation stencil kernels, 3 = round 1's two-barrier tiled kernels instead of the
- * warp-specialised ones, 4 = the staged stencil kernels instead of the ones on TMA box copies.  Process-wide. */
+ * warp-specialised ones, 4 = the staged stencil kernels instead of the ones on TMA box copies (renderer and materialised warp).  Process-wide. */
 int mgr_set_debug_path(int path);
 
 /*

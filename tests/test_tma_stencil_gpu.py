@@ -30,7 +30,7 @@ def _theta(B, L, seed, scale=1.0, px=None, H=None, W=None):
 
 def _run(x, th, go, in_range, dtype, path):
     lib = _lib.load()
-    lib.mgr_set_debug_path(path)
+    _lib.check(lib.mgr_set_debug_path(path), "mgr_set_debug_path")
     try:
         xd = x.to(DEV, dtype).requires_grad_(True)
         td = th.to(DEV).requires_grad_(True)
@@ -73,7 +73,7 @@ def test_tma_translation_16bit_vs_oracle_and_staged(dtype, in_range):
     th = _theta(B, L, 72, 0.7)
     # a back layer that covers the canvas (up to a sub-pixel band): where the composited alpha is ~0 the backward divides by it,
     # and with 16-bit `out` the theta gradient is then noise in ANY implementation (the staged kernels return the same
-    # numbers to the last digit on such stacks -- tools/dbg_theta.py).  Not a whole-pixel shift: grad_theta is one-sided there.
+    # numbers to five digits on such stacks, both far from the fp64 oracle -- tools/dbg_theta.py).  Not a whole-pixel shift: grad_theta is one-sided there.
     th[:, 0, 0, 2] = 0.37 * 2 / W
     th[:, 0, 1, 2] = -0.41 * 2 / H
     go = synth.make_grad_out(B, H, W, seed=72).to(dtype).float()
@@ -180,3 +180,32 @@ def test_tma_mixed_batch_and_fallbacks():
     out8.backward(go.to(DEV, torch.bfloat16))
     assert max_abs(out8.detach().float().cpu().numpy(), new[0]) == 0.0
     assert max_abs(xv8.grad.float().cpu().numpy(), new[1]) == 0.0
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("in_range", ["m11", "01"])
+def test_tma_materialised_warp_of_translation_layers(dtype, in_range):
+    """mgr_warp_forward (what STNv2c returns, fukuwarai/networks.py:250-257): layers that are pure translations take the
+    box-copy kernel, the others the staged one, in the same call; every box alignment, layers pushed off the canvas."""
+    B, H, W = 2, 80, 136
+    px = [(0, 0), (1.5, -2), (-3.25, 7), (5, 5), (-6.5, -9.75), (7, 0), (140, 3), (-20, -90), (63.5, 31.5)]
+    L = len(px) + 1
+    x = synth.make_layers(B, L, H, W, "S", seed=77)
+    if in_range == "01":
+        x = (x + 1) / 2
+    x = x.to(dtype).float()
+    th = _theta(B, L, 77, px=px, H=H, W=W)
+    th[:, L - 1] = synth.make_theta(B, 1, "I", seed=77, cover_back=False)[:, 0]     # one general layer among the translations
+    lib = _lib.load()
+    res = []
+    for path in (0, 4):
+        _lib.check(lib.mgr_set_debug_path(path), "mgr_set_debug_path")
+        try:
+            res.append(mr.warp(x.to(DEV, dtype), th.to(DEV), in_range=in_range).float().cpu().numpy())
+        finally:
+            lib.mgr_set_debug_path(0)
+    ref = R.warp_fwd(x.numpy(), th.numpy(), in_range, np.float64)[0]
+    tol = 5e-6 if dtype == torch.float32 else 2.0 ** -7      # (the staged kernel carries per-pixel fp32 coordinates, the stencil one layer-wide weights)
+    assert max_abs(res[0], res[1]) <= tol
+    assert np.array_equal(res[0][:, L - 1], res[1][:, L - 1])                       # the general layer: the same kernel either way
+    assert max_abs(res[0], ref) <= (FWD_TOL if dtype == torch.float32 else 2.0 ** -7)

@@ -27,6 +27,9 @@ def timeit(fn, n=10):
 
 
 B, L, H, W = 64, 7, 256, 256
+PATH = int(sys.argv[1]) if len(sys.argv) > 1 else 0      # mgr_set_debug_path: 4 = without the kernels on TMA box copies
+from montage_gan_b200 import _lib  # noqa: E402
+_lib.check(_lib.load().mgr_set_debug_path(PATH), 'mgr_set_debug_path')
 for dt in (torch.bfloat16, torch.float32):
     for tf in ("T", "I"):
         x = synth.make_layers(8, L, H, W, "S", seed=0).repeat(8, 1, 1, 1, 1).to("cuda", dt)
@@ -47,5 +50,5 @@ for dt in (torch.bfloat16, torch.float32):
             mr.warp(x, th)
 
         a, b, c = timeit(two_step), timeit(fused), timeit(warp_fwd_only)
-        print(json.dumps({"dtype": str(dt).replace("torch.", ""), "theta": tf, "warp_then_composite_us": round(a, 1), "fused_us": round(b, 1),
+        print(json.dumps({"path": PATH, "dtype": str(dt).replace("torch.", ""), "theta": tf, "warp_then_composite_us": round(a, 1), "fused_us": round(b, 1),
                           "warp_forward_only_us": round(c, 1)}), flush=True)
