@@ -464,25 +464,22 @@ template <typename T>
 int launch_warp_forward(const void* x, const float* theta, void* out, const Geometry& g, cudaStream_t s) {
   if (tiled_ok<T>(x, g)) {                                     // staged footprints, one layer per CTA (warp_tiled.cuh)
     // layers that are pure translations: box copies + planar stencil (render_shift_tma.cuh); the two kernels partition the
-    // layers, on two streams when the batch is big enough for the idle launch to matter (the fork itself costs a general
-    // batch ~10 us at C2 and saves a translation batch ~15: translations are what the placement net emits)
+    // layers.  One stream: forking was measured to cost a general batch more than it saves a translation batch here
+    // (fp32 class-swap step at C2: 1422 vs 1348 us general, 908 vs 912 us translations -- tools/dropin_bench.py)
     CUtensorMap xmap;
     const bool tma = debug_path() != 4 && debug_path() != 2 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
                      shift_tma_x_map<T>(&xmap, x, g, ShiftBox<T>::W, ShiftBox<T>::H);
-    ForkGuard fg;
-    if (tma && use_side_stream(g))
-      if (int rc = fg.fork(s)) return rc;
     dim3 gridt((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B * g.L);
-    warp_fwd_tiled<T><<<gridt, kTiledThreads, sizeof(typename Texel<T>::Vec) * kCapTexels, fg.side_or(s)>>>((const T*)x, theta, (T*)out, g, tma ? 1 : 0);
+    warp_fwd_tiled<T><<<gridt, kTiledThreads, sizeof(typename Texel<T>::Vec) * kCapTexels, s>>>((const T*)x, theta, (T*)out, g, tma ? 1 : 0);
     MGR_CUDA(cudaGetLastError());
     count_launch();
     if (tma) {
       dim3 grids((g.W + kSW - 1) / kSW, (g.H + kSH - 1) / kSH, g.B * g.L);
-      warp_fwd_shift_tma<T><<<grids, kSConsumers, ShiftBox<T>::kStageBytes, s>>>(xmap, theta, (T*)out, g);
+      warp_fwd_shift_tma<T, false><<<grids, kSConsumers, ShiftBox<T>::kStageBytes, s>>>(xmap, theta, (T*)out, g);
       MGR_CUDA(cudaGetLastError());
       count_launch();
     }
-    return fg.join();
+    return MGR_OK;
   }
   dim3 grid((g.W + kTileW - 1) / kTileW, (g.H + kTileH - 1) / kTileH, g.B * g.L);
   warp_fwd_kernel<T><<<grid, kDirectThreads, 0, s>>>((const T*)x, theta, (T*)out, g);
@@ -504,25 +501,39 @@ int launch_warp_backward(const void* x, const float* theta, const void* gout, vo
     int* work = order + (size_t)g.B * g.L + 2;
     int* wcnt = work + (size_t)g.B * g.L;
     int* sflag = wcnt + 2;
+    // grad_x of the layers that are pure translations: the forward's box-copy kernel run as its own adjoint on the upstream
+    // gradient (contiguous [B,L,4,H,W]); the gather below leaves those layers alone.
+    CUtensorMap gmap;
+    Geometry gc = g;
+    gc.sh = g.W; gc.sc = (long long)g.H * g.W; gc.sl = 4 * gc.sc; gc.sb = g.L * gc.sl;
+    const bool tma = nx && debug_path() != 4 && debug_path() != 2 && reinterpret_cast<uintptr_t>(gx) % 16 == 0 &&
+                     shift_tma_x_map<T>(&gmap, gout, gc, ShiftBox<T>::W, ShiftBox<T>::H);
+    if (tma) {
+      dim3 grids((g.W + kSW - 1) / kSW, (g.H + kSH - 1) / kSH, g.B * g.L);
+      warp_fwd_shift_tma<T, true><<<grids, kSConsumers, ShiftBox<T>::kStageBytes, s>>>(gmap, theta, (T*)gx, g);
+      MGR_CUDA(cudaGetLastError());
+      count_launch();
+    }
+    cudaStream_t sg = s;
     if (nx) {
       if (g.B * g.L <= kSmallPlacements) {                       // every layer stays in the work list (skip_shift = 0)
-        placements_small_kernel<<<1, 256, 0, s>>>(theta, inv, g.B, g.L, g.H, g.W, order, work, wcnt, sflag, nullptr, 0);
+        placements_small_kernel<<<1, 256, 0, sg>>>(theta, inv, g.B, g.L, g.H, g.W, order, work, wcnt, sflag, nullptr, 0);
         MGR_CUDA(cudaGetLastError());
         count_launch();
       } else {
-        MGR_CUDA(cudaMemsetAsync(order + g.B * g.L, 0, 2 * sizeof(int), s));
-        inverse_plans_kernel<<<(g.B * g.L + 127) / 128, 128, 0, s>>>(theta, inv, g.B * g.L, g.H, g.W, order, order + g.B * g.L);
-        sample_flags_kernel<<<1, 256, 0, s>>>(inv, g.B, g.L, order, work, wcnt, sflag, 0);
+        MGR_CUDA(cudaMemsetAsync(order + g.B * g.L, 0, 2 * sizeof(int), sg));
+        inverse_plans_kernel<<<(g.B * g.L + 127) / 128, 128, 0, sg>>>(theta, inv, g.B * g.L, g.H, g.W, order, order + g.B * g.L);
+        sample_flags_kernel<<<1, 256, 0, sg>>>(inv, g.B, g.L, order, work, wcnt, sflag, 0);
         MGR_CUDA(cudaGetLastError());
         count_launch(2);
       }
       const long long blocks = (long long)((g.W + 31) / 32) * ((g.H + 31) / 32) * g.B * g.L;
       if (blocks >= 16384) {
         dim3 grid2((g.W + 31) / 32, (g.H + 31) / 32, g.B * g.L);
-        warp_bwd_gather<T, 16><<<grid2, 256, 0, s>>>(inv, work, wcnt, (const T*)gout, (T*)gx, g);
+        warp_bwd_gather<T, 16><<<grid2, 256, 0, sg>>>(inv, work, wcnt, (const T*)gout, (T*)gx, g, tma ? 1 : 0);
       } else {
         dim3 grid2((g.W + 63) / 64, (g.H + 15) / 16, g.B * g.L);
-        warp_bwd_gather<T, 32><<<grid2, 256, 0, s>>>(inv, work, wcnt, (const T*)gout, (T*)gx, g);
+        warp_bwd_gather<T, 32><<<grid2, 256, 0, sg>>>(inv, work, wcnt, (const T*)gout, (T*)gx, g, tma ? 1 : 0);
       }
       MGR_CUDA(cudaGetLastError());
       count_launch();

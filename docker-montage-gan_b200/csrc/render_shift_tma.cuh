@@ -397,20 +397,29 @@ inline bool shift_tma_x_map(CUtensorMap* map, const void* x, const Geometry& g, 
 // tiles with the next box in flight was measured no faster: 109 / 171 us against 109 / 163 us, bf16 / fp32 at C2.)
 namespace mgr {
 
-template <typename T>
+// kAdjoint: the backward of the same op w.r.t. the layer.  The adjoint of a 2 x 2 stencil with weights (1-fx, fx) x (1-fy, fy)
+// at integer shift (X, Y) is the 2 x 2 stencil with weights (fx, 1-fx) x (fy, 1-fy) at shift (-X-1, -Y-1) applied to the
+// upstream gradient, zeros outside the image in either range mode: the same kernel on another plan (`xmap` is then the map
+// over the gradient of the warped layers, `out` is grad_x).  A whole-pixel shift (fx == 0) stays a whole-pixel shift (-X).
+template <typename T, bool kAdjoint>
 __global__ void __launch_bounds__(kSConsumers, 6)
 warp_fwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ theta, T* __restrict__ out, Geometry g) {
   using Box = ShiftBox<T>;
   const int n = blockIdx.z;                                   // b * L + l
   const float* th = theta + (long long)n * 6;
   if (!is_pure_shift(th)) return;
+  if (kAdjoint) g.m11 = 0;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar;
   T* stage = reinterpret_cast<T*>(smem);
   const int tid = threadIdx.x;
   const int b = n / g.L, l = n - b * g.L;
   const int j0 = blockIdx.x * kSW, i0 = blockIdx.y * kSH;
-  const ShiftPlan sp = make_shift_plan(th, g.H, g.W);         // every thread: no broadcast needed, the values are uniform
+  ShiftPlan sp = make_shift_plan(th, g.H, g.W);               // every thread: no broadcast needed, the values are uniform
+  if (kAdjoint) {
+    sp.X = sp.fx == 0.f ? -sp.X : -sp.X - 1; sp.fx = sp.fx == 0.f ? 0.f : 1.f - sp.fx;
+    sp.Y = sp.fy == 0.f ? -sp.Y : -sp.Y - 1; sp.fy = sp.fy == 0.f ? 0.f : 1.f - sp.fy;
+  }
   const int x0 = j0 + sp.X, y0 = i0 + sp.Y;
   const bool miss = shift_box_misses(x0, y0, g.W, g.H);
   const int xa = x0 & ~(Box::kAlign - 1), dx = x0 - xa;

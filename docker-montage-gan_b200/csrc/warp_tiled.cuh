@@ -65,8 +65,9 @@ warp_fwd_tiled(const T* __restrict__ x, const float* __restrict__ theta, T* __re
 template <typename T, int kTX>
 __global__ void __launch_bounds__(256, MGR_P2_BLOCKS)
 warp_bwd_gather(const InverseLayer* __restrict__ plans, const int* __restrict__ work, const int* __restrict__ wcnt,
-                const T* __restrict__ gw, T* __restrict__ gx, Geometry g) {
+                const T* __restrict__ gw, T* __restrict__ gx, Geometry g, int skip_shift) {
   if ((int)blockIdx.z >= wcnt[0]) return;
+  if (skip_shift && plans[work[blockIdx.z]].shift_only) return;      // a translation layer: warp_fwd_shift_tma<T, true> writes its grad_x
   pass2_block<T, false, kTX>(plans, work[blockIdx.z], blockIdx.x * P2Shape<kTX>::kW, blockIdx.y * P2Shape<kTX>::kH,
                              PlanarGrads<T>{gw, 0}, 1.f, gx, nullptr, g);
 }

@@ -196,16 +196,29 @@ def test_tma_materialised_warp_of_translation_layers(dtype, in_range):
     x = x.to(dtype).float()
     th = _theta(B, L, 77, px=px, H=H, W=W)
     th[:, L - 1] = synth.make_theta(B, 1, "I", seed=77, cover_back=False)[:, 0]     # one general layer among the translations
+    gw = torch.randn(B, L, 4, H, W, generator=torch.Generator().manual_seed(77)).to(dtype).float()
     lib = _lib.load()
-    res = []
+    res, grads = [], []
     for path in (0, 4):
         _lib.check(lib.mgr_set_debug_path(path), "mgr_set_debug_path")
         try:
-            res.append(mr.warp(x.to(DEV, dtype), th.to(DEV), in_range=in_range).float().cpu().numpy())
+            xd = x.to(DEV, dtype).requires_grad_(True)
+            td = th.to(DEV).requires_grad_(True)
+            w = mr.warp(xd, td, in_range=in_range)
+            w.backward(gw.to(DEV, dtype))
+            res.append(w.detach().float().cpu().numpy())
+            grads.append((xd.grad.float().cpu().numpy(), td.grad.cpu().numpy()))
         finally:
             lib.mgr_set_debug_path(0)
-    ref = R.warp_fwd(x.numpy(), th.numpy(), in_range, np.float64)[0]
-    tol = 5e-6 if dtype == torch.float32 else 2.0 ** -7      # (the staged kernel carries per-pixel fp32 coordinates, the stencil one layer-wide weights)
+    ref, aux = R.warp_fwd(x.numpy(), th.numpy(), in_range, np.float64)
+    gimg, _, _ = R.grid_sample_bwd((B * L, 4, H, W), aux, gw.numpy().astype(np.float64).reshape(B * L, 4, H, W))
+    f32 = dtype == torch.float32
+    tol = 5e-6 if f32 else 2.0 ** -7                          # (the staged kernel carries per-pixel fp32 coordinates, the stencil one layer-wide weights)
     assert max_abs(res[0], res[1]) <= tol
     assert np.array_equal(res[0][:, L - 1], res[1][:, L - 1])                       # the general layer: the same kernel either way
-    assert max_abs(res[0], ref) <= (FWD_TOL if dtype == torch.float32 else 2.0 ** -7)
+    assert max_abs(res[0], ref) <= (FWD_TOL if f32 else 2.0 ** -7)
+    # backward: grad_x of the translation layers is the same kernel run as its own adjoint on the upstream gradient
+    assert rel_err(grads[0][0], gimg.reshape(x.shape)) <= (GRAD_TOL if f32 else 2.0 ** -7)
+    assert rel_err(grads[0][0], grads[1][0]) <= (1e-5 if f32 else 2.0 ** -7)
+    assert np.array_equal(grads[0][0][:, L - 1], grads[1][0][:, L - 1])
+    assert rel_err(grads[0][1], grads[1][1]) <= 1e-5                                # grad_theta: the same kernel either way
