@@ -543,9 +543,18 @@ int launch_warp_backward(const void* x, const float* theta, const void* gout, vo
       const size_t smem = sizeof(Vec) * kCapTexels + sizeof(float) * kPx * kTiledThreads;
       if (int rc = ensure_dynamic_smem(warp_bwd_theta_tiled<T>, smem)) return rc;
       dim3 gridt((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B * g.L);
-      warp_bwd_theta_tiled<T><<<gridt, kTiledThreads, smem, s>>>((const T*)x, theta, (const T*)gout, gtheta, g);
+      CUtensorMap xmap;
+      const bool tma_t = debug_path() != 4 && debug_path() != 2 && reinterpret_cast<uintptr_t>(gout) % 16 == 0 &&
+                         shift_tma_x_map<T>(&xmap, x, g, ShiftBox<T>::W, ShiftBox<T>::H);
+      warp_bwd_theta_tiled<T><<<gridt, kTiledThreads, smem, s>>>((const T*)x, theta, (const T*)gout, gtheta, g, tma_t ? 1 : 0);
       MGR_CUDA(cudaGetLastError());
       count_launch();
+      if (tma_t) {                                             // translation layers: box copies (render_shift_tma.cuh)
+        dim3 grids((g.W + kSW - 1) / kSW, (g.H + kSH - 1) / kSH, g.B * g.L);
+        warp_bwd_theta_shift_tma<T><<<grids, kSConsumers, ShiftBox<T>::kStageBytes, s>>>(xmap, theta, (const T*)gout, gtheta, g);
+        MGR_CUDA(cudaGetLastError());
+        count_launch();
+      }
     }
     return MGR_OK;
   }

@@ -475,4 +475,113 @@ warp_fwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const float* __rest
   }
 }
 
+// grad_theta of the materialised warp for a translation layer: the box copy of the footprint, d sample / d (ix, iy) from the
+// lerp differences of the four planes (layer-wide weights), contracted with the upstream gradient of the strip's eight pixels
+// (two 8- / 16-byte loads per plane), six sums per thread -> transposing butterfly per warp -> one atomic per (CTA, coefficient).
+template <typename T>
+__global__ void __launch_bounds__(kSConsumers, 3)
+warp_bwd_theta_shift_tma(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ theta, const T* __restrict__ gw,
+                         float* __restrict__ gtheta, Geometry g) {
+  using Box = ShiftBox<T>;
+  const int n = blockIdx.z;
+  const float* th = theta + (long long)n * 6;
+  if (!is_pure_shift(th)) return;
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint64_t bar;
+  __shared__ float s_red[kSConsumers / 32][8];
+  T* stage = reinterpret_cast<T*>(smem);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int b = n / g.L, l = n - b * g.L;
+  const int j0 = blockIdx.x * kSW, i0 = blockIdx.y * kSH;
+  const ShiftPlan sp = make_shift_plan(th, g.H, g.W);
+  const int x0 = j0 + sp.X, y0 = i0 + sp.Y;
+  if (shift_box_misses(x0, y0, g.W, g.H)) return;               // the taps miss the image: no dependence on theta (CTA-uniform)
+  const int xa = x0 & ~(Box::kAlign - 1), dx = x0 - xa;
+  if (tid == 0) {
+    tma_mbar_init(&bar, 1);
+    tma_fence_barrier_init();
+    tma_mbar_expect_tx(&bar, (uint32_t)Box::kBytes);
+    tma_load_5d(stage, &xmap, &bar, xa, y0, 0, l, b);
+  }
+  __syncthreads();
+  const int tx = tid & 15, ty = tid >> 4;
+  const int j = j0 + 4 * tx, i = i0 + 2 * ty;
+  const int hw = g.H * g.W;
+  const bool live[2] = {j < g.W && i < g.H, j < g.W && i + 1 < g.H};
+  // the upstream gradient of the strip, in flight while the box lands
+  f32x2 gq[4][2][2];
+  const T* gp_ = gw + (long long)n * 4 * hw + (long long)i * g.W + j;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float v4[4] = {0.f, 0.f, 0.f, 0.f};
+      if (live[r]) ld_vec<T, 4>(gp_ + c * hw + r * g.W, v4);
+      strip_pack<T>(v4, gq[c][r][0], gq[c][r][1]);
+    }
+  tma_mbar_wait(&bar, 0);
+  if (g.m11 && (xa < 0 || xa + Box::W > g.W || y0 < 0 || y0 + Box::H > g.H)) {         // CTA-uniform
+    shift_patch_oob<T>(stage, xa, y0, g.W, g.H, tid);
+    __syncthreads();
+  }
+  const f32x2 fx2 = bc(sp.fx), fy2 = bc(sp.fy);
+  const T* p = stage + (2 * ty) * Box::W + 4 * tx + (dx & ~3);
+  f32x2 ix[2][2], iy[2][2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) ix[r][0] = ix[r][1] = iy[r][0] = iy[r][1] = bc(0.f);
+  auto body = [&](auto rtag) {
+    constexpr int R = decltype(rtag)::value;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      constexpr int BW = Box::W;
+      f32x2 h0[3], h1[3], d0[3], d1[3];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        f32x2 L0, L1, R0, R1;
+        Row5<T>::template taps<R>(p + c * Box::kPlane + r * BW, 0, L0, L1, R0, R1);
+        d0[r] = sub2(R0, L0); d1[r] = sub2(R1, L1);
+        h0[r] = fma2(fx2, d0[r], L0); h1[r] = fma2(fx2, d1[r], L1);
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        // d/diy = h[r+1] - h[r];  d/dix = lerp_y of the row differences
+        iy[r][0] = fma2(gq[c][r][0], sub2(h0[r + 1], h0[r]), iy[r][0]);
+        iy[r][1] = fma2(gq[c][r][1], sub2(h1[r + 1], h1[r]), iy[r][1]);
+        ix[r][0] = fma2(gq[c][r][0], fma2(fy2, sub2(d0[r + 1], d0[r]), d0[r]), ix[r][0]);
+        ix[r][1] = fma2(gq[c][r][1], fma2(fy2, sub2(d1[r + 1], d1[r]), d1[r]), ix[r][1]);
+      }
+    }
+  };
+  switch (dx & 3) {
+    case 0: body(std::integral_constant<int, 0>{}); break;
+    case 1: body(std::integral_constant<int, 1>{}); break;
+    case 2: body(std::integral_constant<int, 2>{}); break;
+    default: body(std::integral_constant<int, 3>{}); break;
+  }
+  // six sums over the strip (pixels outside the image carry a zero upstream gradient)
+  const float inv_w = 1.f / (float)g.W, inv_h = 1.f / (float)g.H;
+  float xs[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) xs[k] = fmaf((float)(2 * (j + k) + 1), inv_w, -1.f);
+  f32x2 xq0, xq1;
+  strip_pack<T>(xs, xq0, xq1);
+  const float y0n = fmaf((float)(2 * i + 1), inv_h, -1.f), y1n = fmaf((float)(2 * i + 3), inv_h, -1.f);
+  auto hs = [](f32x2 v) { float a, b; upk(v, a, b); return a + b; };
+  const float sx0 = hs(add2(ix[0][0], ix[0][1])), sx1 = hs(add2(ix[1][0], ix[1][1]));
+  const float sy0 = hs(add2(iy[0][0], iy[0][1])), sy1 = hs(add2(iy[1][0], iy[1][1]));
+  const float hW = 0.5f * (float)g.W, hH = 0.5f * (float)g.H;
+  const float th6[6] = {hW * hs(fma2(add2(ix[0][0], ix[1][0]), xq0, mul2(add2(ix[0][1], ix[1][1]), xq1))), hW * fmaf(sx0, y0n, sx1 * y1n), hW * (sx0 + sx1),
+                        hH * hs(fma2(add2(iy[0][0], iy[1][0]), xq0, mul2(add2(iy[0][1], iy[1][1]), xq1))), hH * fmaf(sy0, y0n, sy1 * y1n), hH * (sy0 + sy1)};
+  const float sum = warp_sum6(th6, lane);
+  const int qi = warp_sum6_index(lane);
+  if ((lane & 3) == 0 && qi < 6) s_red[wid][qi] = sum;
+  __syncthreads();
+  if (tid < 6) {
+    float v = 0.f;
+#pragma unroll
+    for (int w = 0; w < kSConsumers / 32; ++w) v += s_red[w][tid];
+    atomicAdd(gtheta + (long long)n * 6 + tid, v);
+  }
+}
+
 }  // namespace mgr

@@ -77,8 +77,9 @@ warp_bwd_gather(const InverseLayer* __restrict__ plans, const int* __restrict__ 
 template <typename T>
 __global__ void __launch_bounds__(kTiledThreads, 3)
 warp_bwd_theta_tiled(const T* __restrict__ x, const float* __restrict__ theta, const T* __restrict__ gw,
-                     float* __restrict__ gtheta, Geometry g) {
+                     float* __restrict__ gtheta, Geometry g, int skip_shift) {
   using Vec = typename Texel<T>::Vec;
+  if (skip_shift && is_pure_shift(theta + (long long)blockIdx.z * 6)) return;      // warp_bwd_theta_shift_tma's layer
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Vec* buf = reinterpret_cast<Vec*>(smem_raw);                                   // [kCapTexels]
   float* stash = reinterpret_cast<float*>(smem_raw + sizeof(Vec) * kCapTexels);  // [kPx][256] partial sums

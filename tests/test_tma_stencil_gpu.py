@@ -188,7 +188,8 @@ def test_tma_materialised_warp_of_translation_layers(dtype, in_range):
     """mgr_warp_forward (what STNv2c returns, fukuwarai/networks.py:250-257): layers that are pure translations take the
     box-copy kernel, the others the staged one, in the same call; every box alignment, layers pushed off the canvas."""
     B, H, W = 2, 80, 136
-    px = [(0, 0), (1.5, -2), (-3.25, 7), (5, 5), (-6.5, -9.75), (7, 0), (140, 3), (-20, -90), (63.5, 31.5)]
+    px = [(0, 0), (1.5, -2.25), (-3.25, 7.5), (5, 5), (-6.5, -9.75), (7, 0), (140, 3), (-20, -90), (63.5, 31.5)]
+    frac = [1, 2, 4, 8]                                         # layers whose shift is fractional along both axes
     L = len(px) + 1
     x = synth.make_layers(B, L, H, W, "S", seed=77)
     if in_range == "01":
@@ -221,4 +222,10 @@ def test_tma_materialised_warp_of_translation_layers(dtype, in_range):
     assert rel_err(grads[0][0], gimg.reshape(x.shape)) <= (GRAD_TOL if f32 else 2.0 ** -7)
     assert rel_err(grads[0][0], grads[1][0]) <= (1e-5 if f32 else 2.0 ** -7)
     assert np.array_equal(grads[0][0][:, L - 1], grads[1][0][:, L - 1])
-    assert rel_err(grads[0][1], grads[1][1]) <= 1e-5                                # grad_theta: the same kernel either way
+    # grad_theta (box-copy kernel for the translation layers): against the oracle and the staged kernel where the derivative is
+    # two-sided (at a whole-pixel shift the cell the one-sided derivative is taken in depends on the last bit of ix)
+    _, ggx, ggy = R.grid_sample_bwd((B * L, 4, H, W), aux, gw.numpy().astype(np.float64).reshape(B * L, 4, H, W))
+    gth = R.affine_grid_bwd(ggx, ggy, np.float64).reshape(B, L, 2, 3)
+    assert rel_err(grads[0][1][:, frac], gth[:, frac]) <= (5e-4 if f32 else 2e-2)
+    assert rel_err(grads[0][1][:, frac], grads[1][1][:, frac]) <= (5e-4 if f32 else 2e-2)
+    assert rel_err(grads[0][1][:, L - 1], grads[1][1][:, L - 1]) <= 1e-5            # the general layer: the same kernel, atomics order only
