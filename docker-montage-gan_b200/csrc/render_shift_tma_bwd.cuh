@@ -1,5 +1,5 @@
-// Fused backward for stacks of pure translations on TMA box copies (16-bit storage; the staged kernel of
-// render_shift.cuh keeps fp32, ragged stacks and odd strides).  Same mathematics as render_bwd_shift -- composite adjoint in
+// Fused backward for stacks of pure translations on TMA box copies (the staged kernel of render_shift.cuh keeps ragged
+// stacks and strides that break TMA's 16-byte rule).  Same mathematics as render_bwd_shift -- composite adjoint in
 // the scalar form of SURVEY.md Appendix A.3, the adjoint of the 2x2 stencil as a 2x2 stencil over per-pixel gradient records
 // exchanged through shared memory, every grad_x element written exactly once, no atomics on grad_x -- rebuilt around what
 // the forward of render_shift_tma.cuh showed: the box copy replaces the staging loop, a thread owns a 4-wide, 2-tall strip
@@ -11,7 +11,8 @@
 //   * one producer lane: at CTA start the saved alphas [L][16][64+], grad_out and out [4][16][64+] of the tile (three box
 //     copies on one mbarrier), then the x footprints {64+ x 17 x 4} of the layers through a two-stage ring;
 //   * pre-pass: transmittances T_l front to back from the saved alphas, written back IN PLACE of the alpha samples (the
-//     main loop re-samples alpha from x and only needs T_l), and (G_P, G_A) per pixel into a thread-private shared slot;
+//     main loop re-samples alpha from x and only needs T_l), and (G_P, G_A) per pixel into a thread-private shared slot
+//     (kGlobalT -- fp32 tensors, 16-bit stacks past 19 layers: no pixel-space boxes, T_l parked in the workspace instead);
 //   * per layer: sample alpha, then the colours channel by channel folding each into u = G_P.c + G_A and into the
 //     G_P-weighted coordinate derivatives, so no channel's samples stay live; records (T a G_P, dA) to shared memory, one
 //     barrier, stencil adjoint with the layer-uniform weights, stores; the six theta sums of the layer are reduced in the warp
