@@ -128,6 +128,19 @@ def test_new_entry_points_validate_before_touching_memory():
     assert lib.mgr_warp_backward(0x1000, None, 0x3000, 0x2000, 0x4000, 0x5000, None, 0, 2, 3, 8, 8, 0, 0, 3, None) == 3
 
 
+def test_debug_path_setter_accepts_every_documented_path():
+    """include/montage_render.h documents paths 0..4 (4 = the staged stencil kernels instead of the ones on TMA box copies).
+    The setter once rejected 4 while its callers ignored the return code, so an A/B run compared a kernel with itself."""
+    lib = _lib.load()
+    try:
+        for path in range(5):
+            assert lib.mgr_set_debug_path(path) == 0, path
+        assert lib.mgr_set_debug_path(5) == 1 and b"debug path" in lib.mgr_last_error()
+        assert lib.mgr_set_debug_path(-1) == 1
+    finally:
+        lib.mgr_set_debug_path(0)
+
+
 def test_augment_geom_entry_points_validate():
     lib = _lib.load()
     B, C, H, W, m = 2, 4, 16, 16, (3, 2, 1, 0)
