@@ -102,10 +102,12 @@ const char* ragged_problem(const SrcLayers& src, const DstLayers* dst, const Geo
 }
 
 // fork the general kernels onto the side stream?  Only where an idle launch costs more than the fork / join (four runtime
-// calls): from about a million layer-pixels; MGR_NO_SIDE_STREAM=1 in the environment keeps everything on one stream
+// calls): from a million layer-pixels (measured: at 3.7 M -- C1 -- translations gain 10 %, general placements lose nothing; at 0.9 M
+// general placements lose 7 %); MGR_NO_SIDE_STREAM=1 in the environment keeps everything on one stream
 inline bool use_side_stream(const Geometry& g) {
   static const bool off = [] { const char* e = getenv("MGR_NO_SIDE_STREAM"); return e && e[0] == '1'; }();
-  return !off && (long long)g.B * g.L * g.H * g.W >= (1LL << 22);
+  static const long long min_px = [] { const char* e = getenv("MGR_SIDE_STREAM_MIN"); return e ? atoll(e) : (1LL << 20); }();   // developer knob
+  return !off && (long long)g.B * g.L * g.H * g.W >= min_px;
 }
 
 // joins on every exit path (an early error return must not leave the side stream dangling off `s`, least of all in a capture)
