@@ -19,6 +19,10 @@
 #include <map>
 #include <utility>
 
+#ifndef MGR_STB_SMEM_CAP
+#define MGR_STB_SMEM_CAP (100 * 1024)      // the stencil backward's tile state must leave room for two CTAs per SM
+#endif
+
 namespace mgr {
 
 // Opt a kernel in to more than 48 KB of dynamic shared memory when a launch first needs it (and again only if a later
@@ -363,10 +367,10 @@ int backward_tiled(const void* x, const SrcLayers& src, const float* theta, cons
 #ifdef MGR_STB_FORCE_GLOBAL_T
     const bool global_t = true;
 #else
-    const bool global_t = sizeof(T) == 4 || bwd_tma_layout<T>(g.L, false).total > 100 * 1024;
+    const bool global_t = sizeof(T) == 4 || bwd_tma_layout<T>(g.L, false).total > MGR_STB_SMEM_CAP;
 #endif
     const BwdSmem lay = bwd_tma_layout<T>(g.L, global_t);
-    if (shift && debug_path() != 4 && (size_t)lay.total <= 100 * 1024 && (!nx || reinterpret_cast<uintptr_t>(dst.s[0].ptr) % 16 == 0) &&
+    if (shift && debug_path() != 4 && (size_t)lay.total <= MGR_STB_SMEM_CAP && (!nx || reinterpret_cast<uintptr_t>(dst.s[0].ptr) % 16 == 0) &&
         bwd_tma_maps<T>(&xmap, &amap, &gmap, &omap, x, sav, gout, out, g, global_t)) {
       shift_tma = true;
       dim3 grid4((g.W + 1 + kBAncW - 1) / kBAncW, (g.H + 1 + kBAncH - 1) / kBAncH, g.B);

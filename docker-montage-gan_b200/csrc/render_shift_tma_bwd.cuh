@@ -31,9 +31,12 @@
 
 namespace mgr {
 
-constexpr int kBW = 64, kBH = 16;                 // pixel tile
+#ifndef MGR_STB_TILE_H
+#define MGR_STB_TILE_H 16
+#endif
+constexpr int kBW = 64, kBH = MGR_STB_TILE_H;     // pixel tile (height a multiple of 4: whole warps of 16 x 2 strips)
 constexpr int kBAncW = kBW - 1, kBAncH = kBH - 1; // anchors a CTA owns
-constexpr int kBConsumers = 128;                  // 16 x 8 strips of 4 x 2 pixels
+constexpr int kBConsumers = 8 * kBH;              // 16 x (kBH / 2) strips of 4 x 2 pixels
 constexpr int kBThreads = kBConsumers + 32;
 constexpr int kBStages = MGR_STB_STAGES;
 
@@ -384,7 +387,7 @@ render_bwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const __grid_cons
         for (int k = 0; k < 4; ++k) cm |= (cx + k < sp.X || cx + k > sp.X + g.W) ? (1u << k) : 0u;
 #pragma unroll
         for (int rr = 0; rr < 2; ++rr) {
-          const int yy = zy0 + ty + 8 * rr;
+          const int yy = zy0 + ty + (kBH / 2) * rr;
           if (yy >= g.H) continue;
           const unsigned m = (yy < sp.Y || yy > sp.Y + g.H) ? 0xfu : cm;
           if (m == 0u) continue;
