@@ -474,14 +474,14 @@ int launch_warp_forward(const void* x, const float* theta, void* out, const Geom
     // (fp32 class-swap step at C2: 1422 vs 1348 us general, 908 vs 912 us translations -- tools/dropin_bench.py)
     CUtensorMap xmap;
     const bool tma = debug_path() != 4 && debug_path() != 2 && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
-                     shift_tma_x_map<T>(&xmap, x, g, ShiftBox<T>::W, ShiftBox<T>::H);
+                     shift_tma_x_map<T>(&xmap, x, g, ShiftBox<T, kWTH>::W, ShiftBox<T, kWTH>::H);
     dim3 gridt((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B * g.L);
     warp_fwd_tiled<T><<<gridt, kTiledThreads, sizeof(typename Texel<T>::Vec) * kCapTexels, s>>>((const T*)x, theta, (T*)out, g, tma ? 1 : 0);
     MGR_CUDA(cudaGetLastError());
     count_launch();
     if (tma) {
-      dim3 grids((g.W + kSW - 1) / kSW, (g.H + kSH - 1) / kSH, g.B * g.L);
-      warp_fwd_shift_tma<T, false><<<grids, kSConsumers, ShiftBox<T>::kStageBytes, s>>>(xmap, theta, (T*)out, g);
+      dim3 grids((g.W + kSW - 1) / kSW, (g.H + kWTH - 1) / kWTH, g.B * g.L);
+      warp_fwd_shift_tma<T, false><<<grids, kWConsumers, ShiftBox<T, kWTH>::kStageBytes, s>>>(xmap, theta, (T*)out, g);
       MGR_CUDA(cudaGetLastError());
       count_launch();
     }
@@ -513,10 +513,10 @@ int launch_warp_backward(const void* x, const float* theta, const void* gout, vo
     Geometry gc = g;
     gc.sh = g.W; gc.sc = (long long)g.H * g.W; gc.sl = 4 * gc.sc; gc.sb = g.L * gc.sl;
     const bool tma = nx && debug_path() != 4 && debug_path() != 2 && reinterpret_cast<uintptr_t>(gx) % 16 == 0 &&
-                     shift_tma_x_map<T>(&gmap, gout, gc, ShiftBox<T>::W, ShiftBox<T>::H);
+                     shift_tma_x_map<T>(&gmap, gout, gc, ShiftBox<T, kWTH>::W, ShiftBox<T, kWTH>::H);
     if (tma) {
-      dim3 grids((g.W + kSW - 1) / kSW, (g.H + kSH - 1) / kSH, g.B * g.L);
-      warp_fwd_shift_tma<T, true><<<grids, kSConsumers, ShiftBox<T>::kStageBytes, s>>>(gmap, theta, (T*)gx, g);
+      dim3 grids((g.W + kSW - 1) / kSW, (g.H + kWTH - 1) / kWTH, g.B * g.L);
+      warp_fwd_shift_tma<T, true><<<grids, kWConsumers, ShiftBox<T, kWTH>::kStageBytes, s>>>(gmap, theta, (T*)gx, g);
       MGR_CUDA(cudaGetLastError());
       count_launch();
     }
@@ -551,13 +551,13 @@ int launch_warp_backward(const void* x, const float* theta, const void* gout, vo
       dim3 gridt((g.W + kTW - 1) / kTW, (g.H + kTH - 1) / kTH, g.B * g.L);
       CUtensorMap xmap;
       const bool tma_t = debug_path() != 4 && debug_path() != 2 && reinterpret_cast<uintptr_t>(gout) % 16 == 0 &&
-                         shift_tma_x_map<T>(&xmap, x, g, ShiftBox<T>::W, ShiftBox<T>::H);
+                         shift_tma_x_map<T>(&xmap, x, g, ShiftBox<T, kWTH>::W, ShiftBox<T, kWTH>::H);
       warp_bwd_theta_tiled<T><<<gridt, kTiledThreads, smem, s>>>((const T*)x, theta, (const T*)gout, gtheta, g, tma_t ? 1 : 0);
       MGR_CUDA(cudaGetLastError());
       count_launch();
       if (tma_t) {                                             // translation layers: box copies (render_shift_tma.cuh)
-        dim3 grids((g.W + kSW - 1) / kSW, (g.H + kSH - 1) / kSH, g.B * g.L);
-        warp_bwd_theta_shift_tma<T><<<grids, kSConsumers, ShiftBox<T>::kStageBytes, s>>>(xmap, theta, (const T*)gout, gtheta, g);
+        dim3 grids((g.W + kSW - 1) / kSW, (g.H + kWTH - 1) / kWTH, g.B * g.L);
+        warp_bwd_theta_shift_tma<T><<<grids, kWConsumers, ShiftBox<T, kWTH>::kStageBytes, s>>>(xmap, theta, (const T*)gout, gtheta, g);
         MGR_CUDA(cudaGetLastError());
         count_launch();
       }

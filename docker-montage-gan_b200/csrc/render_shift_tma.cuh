@@ -27,20 +27,23 @@
 #define MGR_STF_STAGES16 4
 #endif
 #ifndef MGR_STF_BLOCKS
-#define MGR_STF_BLOCKS 2
+#define MGR_STF_BLOCKS 4
 #endif
 
 namespace mgr {
 
-constexpr int kSW = 64, kSH = 32;                 // output tile of the TMA stencil forward
-constexpr int kSConsumers = 256;                  // 16 x 16 strips of 4 x 2 pixels
+#ifndef MGR_STF_TILE_H
+#define MGR_STF_TILE_H 16
+#endif
+constexpr int kSW = 64, kSH = MGR_STF_TILE_H;     // output tile of the TMA stencil forward (height a multiple of 4)
+constexpr int kSConsumers = 8 * kSH;              // 16 x (kSH / 2) strips of 4 x 2 pixels
 constexpr int kSThreads = kSConsumers + 32;       // + the producer warp
 constexpr int kSMaxStages = 4;
 
-template <typename T> struct ShiftBox {
+template <typename T, int TH = kSH> struct ShiftBox {
   static constexpr int kAlign = 16 / (int)sizeof(T);        // the box starts on a 16-byte boundary of the row
   static constexpr int W = kSW + kAlign;                    // tile + 1 tap columns + up to kAlign - 1 columns of alignment slack
-  static constexpr int H = kSH + 1;
+  static constexpr int H = TH + 1;
   static constexpr int kPlane = W * H;                      // elements per channel plane
   static constexpr int kBytes = kPlane * 4 * (int)sizeof(T);
   static constexpr int kStageBytes = (kBytes + 127) & ~127; // stages start on 128-byte boundaries
@@ -48,8 +51,9 @@ template <typename T> struct ShiftBox {
 };
 
 // the taps of the tile (columns x0 .. x0 + kSW, rows y0 .. y0 + kSH) all miss the image: the layer is transparent here
+template <int TH = kSH>
 __device__ __forceinline__ bool shift_box_misses(int x0, int y0, int W, int H) {
-  return x0 + kSW < 0 || x0 >= W || y0 + kSH < 0 || y0 >= H;
+  return x0 + kSW < 0 || x0 >= W || y0 + TH < 0 || y0 >= H;
 }
 
 // ---- five adjacent texels e0..e4 of one channel row -> the x-lerped values of the strip's four pixels ------------------
@@ -166,17 +170,17 @@ template <> __device__ __forceinline__ __half raw_minus_one<__half>() { return _
 
 // [-1,1] range mode: texels of the box outside the image become the padding value -1 (the copy zero-fills them).
 // Threads 0..255 of the consumer group.
-template <typename T>
+template <typename T, int TH = kSH>
 __device__ __forceinline__ void shift_patch_oob(T* stage, int x0, int y0, int W, int H, int tid) {   // (x0, y0): texel of box element (0, 0)
-  constexpr int BW = ShiftBox<T>::W, BH = ShiftBox<T>::H, NC = ShiftBox<T>::W;
+  constexpr int BW = ShiftBox<T, TH>::W, BH = ShiftBox<T, TH>::H, NC = ShiftBox<T, TH>::W;
   const int nT = min(max(-y0, 0), BH), nB = min(max(y0 + BH - H, 0), BH);
   const int nL = min(max(-x0, 0), NC), nR = min(max(x0 + NC - W, 0), NC);
   const T m1 = raw_minus_one<T>();
   const int cl = tid & 7;                                     // 8 column lanes x 32 (row, channel) lanes
 #pragma unroll 1
-  for (int rc = tid >> 3; rc < 4 * BH; rc += kSConsumers / 8) {
+  for (int rc = tid >> 3; rc < 4 * BH; rc += TH) {                // 8 TH threads take part
     const int r = rc >> 2, c = rc & 3;
-    T* row = stage + c * ShiftBox<T>::kPlane + r * BW;
+    T* row = stage + c * ShiftBox<T, TH>::kPlane + r * BW;
     if (r < nT || r >= BH - nB) {
 #pragma unroll 1
       for (int k = cl; k < NC; k += 8) row[k] = m1;
@@ -230,7 +234,7 @@ inline size_t shift_tma_fwd_smem_bytes(int L) {
 }
 
 template <typename T, bool kSave>
-__global__ void __launch_bounds__(kSThreads, sizeof(T) == 4 ? 2 : MGR_STF_BLOCKS)
+__global__ void __launch_bounds__(kSThreads, MGR_STF_BLOCKS)
 render_fwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ theta, T* __restrict__ out,
                      typename SavedAlpha<T>::type* __restrict__ sav, Geometry g, const int* __restrict__ shift_flags) {
   using SA = typename SavedAlpha<T>::type;
@@ -390,6 +394,8 @@ inline bool shift_tma_x_map(CUtensorMap* map, const void* x, const Geometry& g, 
 
 }  // namespace mgr
 
+constexpr int kWTH = 32, kWConsumers = 8 * kWTH;          // the materialised-warp kernels keep 64 x 32 tiles (64 x 16: +7 % on the warp forward)
+
 // ---- materialised warp of pure-translation LAYERS (what STNv2c / STNv2b return, fukuwarai/networks.py:250-257, and what
 // random_position computes, custom_utils/image_utils.py:281-294) on the same box copy: one (layer, 64 x 32 tile) per CTA, the
 // raw bilinear lerp of the four planes written out.  The decision is per LAYER here (each layer is warped on its own): CTAs
@@ -402,9 +408,9 @@ namespace mgr {
 // upstream gradient, zeros outside the image in either range mode: the same kernel on another plan (`xmap` is then the map
 // over the gradient of the warped layers, `out` is grad_x).  A whole-pixel shift (fx == 0) stays a whole-pixel shift (-X).
 template <typename T, bool kAdjoint>
-__global__ void __launch_bounds__(kSConsumers, 6)
+__global__ void __launch_bounds__(kWConsumers, 6)
 warp_fwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ theta, T* __restrict__ out, Geometry g) {
-  using Box = ShiftBox<T>;
+  using Box = ShiftBox<T, kWTH>;
   const int n = blockIdx.z;                                   // b * L + l
   const float* th = theta + (long long)n * 6;
   if (!is_pure_shift(th)) return;
@@ -414,14 +420,14 @@ warp_fwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const float* __rest
   T* stage = reinterpret_cast<T*>(smem);
   const int tid = threadIdx.x;
   const int b = n / g.L, l = n - b * g.L;
-  const int j0 = blockIdx.x * kSW, i0 = blockIdx.y * kSH;
+  const int j0 = blockIdx.x * kSW, i0 = blockIdx.y * kWTH;
   ShiftPlan sp = make_shift_plan(th, g.H, g.W);               // every thread: no broadcast needed, the values are uniform
   if (kAdjoint) {
     sp.X = sp.fx == 0.f ? -sp.X : -sp.X - 1; sp.fx = sp.fx == 0.f ? 0.f : 1.f - sp.fx;
     sp.Y = sp.fy == 0.f ? -sp.Y : -sp.Y - 1; sp.fy = sp.fy == 0.f ? 0.f : 1.f - sp.fy;
   }
   const int x0 = j0 + sp.X, y0 = i0 + sp.Y;
-  const bool miss = shift_box_misses(x0, y0, g.W, g.H);
+  const bool miss = shift_box_misses<kWTH>(x0, y0, g.W, g.H);
   const int xa = x0 & ~(Box::kAlign - 1), dx = x0 - xa;
   if (tid == 0 && !miss) {
     tma_mbar_init(&bar, 1);
@@ -448,7 +454,7 @@ warp_fwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const float* __rest
   }
   tma_mbar_wait(&bar, 0);
   if (g.m11 && (xa < 0 || xa + Box::W > g.W || y0 < 0 || y0 + Box::H > g.H)) {         // CTA-uniform
-    shift_patch_oob<T>(stage, xa, y0, g.W, g.H, tid);
+    shift_patch_oob<T, kWTH>(stage, xa, y0, g.W, g.H, tid);
     __syncthreads();
   }
   const f32x2 fx2 = bc(sp.fx), fy2 = bc(sp.fy);
@@ -479,23 +485,23 @@ warp_fwd_shift_tma(const __grid_constant__ CUtensorMap xmap, const float* __rest
 // lerp differences of the four planes (layer-wide weights), contracted with the upstream gradient of the strip's eight pixels
 // (two 8- / 16-byte loads per plane), six sums per thread -> transposing butterfly per warp -> one atomic per (CTA, coefficient).
 template <typename T>
-__global__ void __launch_bounds__(kSConsumers, 3)
+__global__ void __launch_bounds__(kWConsumers, 3)
 warp_bwd_theta_shift_tma(const __grid_constant__ CUtensorMap xmap, const float* __restrict__ theta, const T* __restrict__ gw,
                          float* __restrict__ gtheta, Geometry g) {
-  using Box = ShiftBox<T>;
+  using Box = ShiftBox<T, kWTH>;
   const int n = blockIdx.z;
   const float* th = theta + (long long)n * 6;
   if (!is_pure_shift(th)) return;
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint64_t bar;
-  __shared__ float s_red[kSConsumers / 32][8];
+  __shared__ float s_red[kWConsumers / 32][8];
   T* stage = reinterpret_cast<T*>(smem);
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int b = n / g.L, l = n - b * g.L;
-  const int j0 = blockIdx.x * kSW, i0 = blockIdx.y * kSH;
+  const int j0 = blockIdx.x * kSW, i0 = blockIdx.y * kWTH;
   const ShiftPlan sp = make_shift_plan(th, g.H, g.W);
   const int x0 = j0 + sp.X, y0 = i0 + sp.Y;
-  if (shift_box_misses(x0, y0, g.W, g.H)) return;               // the taps miss the image: no dependence on theta (CTA-uniform)
+  if (shift_box_misses<kWTH>(x0, y0, g.W, g.H)) return;               // the taps miss the image: no dependence on theta (CTA-uniform)
   const int xa = x0 & ~(Box::kAlign - 1), dx = x0 - xa;
   if (tid == 0) {
     tma_mbar_init(&bar, 1);
@@ -521,7 +527,7 @@ warp_bwd_theta_shift_tma(const __grid_constant__ CUtensorMap xmap, const float* 
     }
   tma_mbar_wait(&bar, 0);
   if (g.m11 && (xa < 0 || xa + Box::W > g.W || y0 < 0 || y0 + Box::H > g.H)) {         // CTA-uniform
-    shift_patch_oob<T>(stage, xa, y0, g.W, g.H, tid);
+    shift_patch_oob<T, kWTH>(stage, xa, y0, g.W, g.H, tid);
     __syncthreads();
   }
   const f32x2 fx2 = bc(sp.fx), fy2 = bc(sp.fy);
@@ -579,7 +585,7 @@ warp_bwd_theta_shift_tma(const __grid_constant__ CUtensorMap xmap, const float* 
   if (tid < 6) {
     float v = 0.f;
 #pragma unroll
-    for (int w = 0; w < kSConsumers / 32; ++w) v += s_red[w][tid];
+    for (int w = 0; w < kWConsumers / 32; ++w) v += s_red[w][tid];
     atomicAdd(gtheta + (long long)n * 6 + tid, v);
   }
 }
